@@ -1,0 +1,236 @@
+"""HOT PATH 2, host side: the modified-CBOW trainer behind the reference's call
+``compute_genetovec(pathList, n_genes, hidden_size, learning_rate)`` (/root/reference/G2Vec.py:74,
+217-286).  The TF1 graph (two matmuls, sigmoid BCE, Adam, accuracy; :231-251) is replaced by the
+fused kernels of csrc/g2v_cbow.cu called through the C ABI; this module keeps what the reference
+keeps in Python: shuffle + 80/20 split (:219-226), the epoch loop, the log lines and the early stop
+(:259-284).
+
+Multi-GPU (one process per GPU, torch.distributed/NCCL): the parameters are replicated, the
+training and validation windows are sharded over the ranks, and the dense gradient is all-reduced
+once per optimizer step before every rank applies the identical update.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+# ------------------------------------------------------------------------------ host-side pieces
+def split_indices(n, seed):
+    """``np.random.shuffle(pathList)`` then ``pivot = int(len * 0.8)`` (G2Vec.py:219-222), done on an
+    index vector with the same legacy MT19937 stream (RandomState(seed).shuffle)."""
+    perm = np.arange(n, dtype=np.int64)
+    np.random.RandomState(seed).shuffle(perm)
+    pivot = int(n * 0.8)
+    return perm[:pivot], perm[pivot:]
+
+
+def truncated_normal(shape, stddev, rng):
+    """tf.truncated_normal (G2Vec.py:234-235): N(0, stddev) re-drawn while |x| > 2 stddev."""
+    x = rng.standard_normal(size=shape)
+    bad = np.abs(x) > 2.0
+    while bad.any():
+        x[bad] = rng.standard_normal(size=int(bad.sum()))
+        bad = np.abs(x) > 2.0
+    return (x * stddev).astype(np.float32)
+
+
+def init_weights(n_genes, hidden, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    s = 1.0 / math.sqrt(hidden)
+    return truncated_normal((n_genes, hidden), s, rng), truncated_normal((hidden,), s, rng)
+
+
+def shard_by_nnz(idx, lens, world, rank):
+    """Deal window indices to ranks so every rank gets ~equal gather work: sort by length
+    (descending, stable) and deal round-robin."""
+    if world == 1:
+        return idx
+    order = np.argsort(-lens[idx], kind="stable")
+    return idx[order][rank::world]
+
+
+# ------------------------------------------------------------------------------------ the model
+class CbowModel:
+    """Parameters + optimizer state + scratch in HBM, and the three kernel calls."""
+
+    def __init__(self, rowptr, gene, label, n_genes, hidden, W_ih0, W_ho0, optimizer="adam", reduce="sum",
+                 lr=0.005, beta1=0.9, beta2=0.999, eps=1e-8, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("g2vec_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _capi.load()
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+
+        def to(a, dt):
+            if isinstance(a, torch.Tensor):
+                return a.to(device=dev, dtype=dt).contiguous()
+            return torch.from_numpy(np.ascontiguousarray(a)).to(device=dev, dtype=dt)
+
+        self.rowptr = to(rowptr, torch.int32)
+        self.gene = to(gene, torch.int32)
+        self.label = to(label, torch.uint8)
+        self.V, self.D = int(n_genes), int(hidden)
+        self.W_ih = to(W_ih0, torch.float32).reshape(self.V, self.D).clone()
+        self.W_ho = to(W_ho0, torch.float32).reshape(self.D).clone()
+        self.opt = {"adam": _capi.OPT_ADAM_TF1, "sgd": _capi.OPT_SGD}[optimizer]
+        self.reduce = {"sum": _capi.REDUCE_SUM, "mean": _capi.REDUCE_MEAN}[reduce]
+        self.lr, self.beta1, self.beta2, self.eps = float(lr), float(beta1), float(beta2), float(eps)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.g_ih, self.g_ho = z(self.V, self.D), z(self.D)
+        if self.opt == _capi.OPT_ADAM_TF1:
+            self.m_ih, self.v_ih, self.m_ho, self.v_ho = z(self.V, self.D), z(self.V, self.D), z(self.D), z(self.D)
+        else:
+            self.m_ih = self.v_ih = self.m_ho = self.v_ho = None
+        # [loss_sum (f64 bits), n_correct_train_fwd, n_correct_val, n_correct_train] as 4 x 8 bytes
+        self.acc = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.t = 0
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @staticmethod
+    def _ptr(t):
+        return 0 if t is None else t.data_ptr()
+
+    def fwdbwd(self, win, n_total, win_begin=0, n_win=None):
+        """Accumulate the gradient of the listed windows into g_ih / g_ho (loss sum -> acc[0],
+        pre-update correct count -> acc[1])."""
+        n = (win.shape[0] - win_begin) if n_win is None else n_win
+        rc = self.lib.g2v_cbow_fwdbwd(self.rowptr.data_ptr(), self.gene.data_ptr(), self.label.data_ptr(),
+                                      self._ptr(win), int(win_begin), int(n), 1.0 / float(n_total),
+                                      self.W_ih.data_ptr(), self.W_ho.data_ptr(), self.g_ih.data_ptr(),
+                                      self.g_ho.data_ptr(), self.acc.data_ptr(), self.acc.data_ptr() + 8,
+                                      self.V, self.D, self.reduce, self._stream())
+        _capi.check(rc, "g2v_cbow_fwdbwd")
+
+    def update(self):
+        self.t += 1
+        rc = self.lib.g2v_cbow_update(self.W_ih.data_ptr(), self.W_ho.data_ptr(), self._ptr(self.m_ih),
+                                      self._ptr(self.v_ih), self._ptr(self.m_ho), self._ptr(self.v_ho),
+                                      self.g_ih.data_ptr(), self.g_ho.data_ptr(), self.V, self.D, self.opt,
+                                      self.lr, self.beta1, self.beta2, self.eps, self.t, self._stream())
+        _capi.check(rc, "g2v_cbow_update")
+
+    def evaluate(self, win, slot, win_begin=0, n_win=None):
+        """Add the number of correctly classified listed windows into acc[slot]."""
+        n = (win.shape[0] - win_begin) if n_win is None else n_win
+        rc = self.lib.g2v_cbow_eval(self.rowptr.data_ptr(), self.gene.data_ptr(), self.label.data_ptr(),
+                                    self._ptr(win), int(win_begin), int(n), self.W_ih.data_ptr(),
+                                    self.W_ho.data_ptr(), self.acc.data_ptr() + 8 * slot, self.V, self.D,
+                                    self.reduce, self._stream())
+        _capi.check(rc, "g2v_cbow_eval")
+
+    def loss_sum(self, acc_host):
+        return float(acc_host[:1].view(torch.float64)[0])
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500, seed=0, optimizer="adam",
+               reduce="sum", W_ih0=None, W_ho0=None, split=None, early_stop=True, log=print, return_info=False):
+    """Train the modified CBOW on CSR windows and return W_ih (np.float32 [n_genes, hidden]) exactly as
+    ``compute_genetovec`` does: the weights after the last step whose validation accuracy did not drop.
+
+    ``max_epoch`` is the reference's ``--epoch`` (parsed at G2Vec.py:515 but ignored there; the loop is
+    hard-coded ``range(500)`` at :262) -- the default 500 reproduces the reference.
+    """
+    dist = _dist()
+    world, rank = (dist.get_world_size(), dist.get_rank()) if dist else (1, 0)
+    rowptr_np = (win_rowptr.cpu().numpy() if isinstance(win_rowptr, torch.Tensor) else np.asarray(win_rowptr))
+    N = rowptr_np.shape[0] - 1
+    if N < 2:
+        raise ValueError("need at least two context windows")
+    tr, va = split_indices(N, seed) if split is None else split
+    if W_ih0 is None or W_ho0 is None:
+        W_ih0, W_ho0 = init_weights(n_genes, hidden, seed)
+    model = CbowModel(win_rowptr, win_gene, labels, n_genes, hidden, W_ih0, W_ho0, optimizer, reduce, lr)
+    lens = np.diff(rowptr_np).astype(np.int64)
+    n_tr, n_va = len(tr), len(va)
+    tr_loc, va_loc = shard_by_nnz(np.asarray(tr), lens, world, rank), shard_by_nnz(np.asarray(va), lens, world, rank)
+    dev = model.device
+    tr_d = torch.from_numpy(np.ascontiguousarray(tr_loc, dtype=np.int32)).to(dev)
+    va_d = torch.from_numpy(np.ascontiguousarray(va_loc, dtype=np.int32)).to(dev)
+
+    if log:
+        log("     Start training the modified CBOW with early stopping")
+    t0 = time.time()
+    before_val, before_tr = np.float32(-1.0), np.float32(0.0)
+    result = model.W_ih.clone()
+    hist, stop = [], None
+    for step in range(max_epoch):
+        model.acc.zero_()
+        if len(tr_loc):
+            model.fwdbwd(tr_d, n_tr)
+        if dist:
+            dist.all_reduce(model.g_ih)
+            dist.all_reduce(model.g_ho)
+        model.update()
+        if len(va_loc):
+            model.evaluate(va_d, 2)
+        if len(tr_loc):
+            model.evaluate(tr_d, 3)
+        if dist:
+            dist.all_reduce(model.acc[2:4])
+        acc = model.acc.cpu()                                   # the step's only host sync
+        acc_val = np.float32(int(acc[2])) / np.float32(max(n_va, 1))
+        acc_tr = np.float32(int(acc[3])) / np.float32(max(n_tr, 1))
+        hist.append((step, float(acc_val), float(acc_tr)))
+        if step % 5 == 0 and log:
+            t1 = time.time()
+            log("    - Epoch: %03d\tACC[val]=%.4f\tACC[tr]=%.4f (%.3f sec)" % (step, acc_val, acc_tr, t1 - t0))
+            t0 = time.time()
+        if early_stop and acc_val < before_val:
+            if log:
+                log("    - Epoch(stop): %03d\tACC[val]=%.4f\tACC[tr]=%.4f (%.3f sec)"
+                    % (step - 1, before_val, before_tr, time.time() - t0))
+            stop = step
+            break
+        before_val, before_tr = acc_val, acc_tr
+        result.copy_(model.W_ih)
+    if log:
+        log("    Optimization Finish")
+    out = result.cpu().numpy()
+    if return_info:
+        return out, {"history": hist, "stop_step": stop, "n_train": n_tr, "n_val": n_va, "model": model}
+    return out
+
+
+def compute_genetovec(pathList, n_genes, hidden_size, learning_rate, max_epoch=500, seed=0, log=print):
+    """Drop-in for the reference signature (G2Vec.py:217): dense ``pathList`` [N, n_genes+1] in
+    (last column = label), W_ih out."""
+    from .paths import dense_pathlist_to_csr
+    rowptr, gene, label = dense_pathlist_to_csr(pathList)
+    return train_cbow(rowptr, gene, label, n_genes, hidden_size, learning_rate, max_epoch=max_epoch, seed=seed,
+                      log=log)
+
+
+def cbow_step_host(rowptr, gene, label, W_ih, W_ho, state=None, lr=0.005, t=1, optimizer="adam", reduce="sum",
+                   beta1=0.9, beta2=0.999, eps=1e-8):
+    """One full-batch step through ``g2v_cbow_step_host``: NumPy in, NumPy updated in place."""
+    lib = _capi.load()
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); gene = np.ascontiguousarray(gene, dtype=np.int32)
+    label = np.ascontiguousarray(label, dtype=np.uint8)
+    V, D = W_ih.shape
+    for a in (W_ih, W_ho):
+        assert a.dtype == np.float32 and a.flags.c_contiguous
+    opt = {"adam": _capi.OPT_ADAM_TF1, "sgd": _capi.OPT_SGD}[optimizer]
+    if opt == _capi.OPT_ADAM_TF1 and state is None:
+        state = [np.zeros_like(W_ih), np.zeros_like(W_ih), np.zeros_like(W_ho), np.zeros_like(W_ho)]
+    p = lambda a: 0 if a is None else a.ctypes.data
+    m_ih, v_ih, m_ho, v_ho = state if state is not None else (None,) * 4
+    loss = np.zeros(1, dtype=np.float64); nc = np.zeros(1, dtype=np.int64)
+    rc = lib.g2v_cbow_step_host(rowptr.ctypes.data, gene.ctypes.data, label.ctypes.data, rowptr.shape[0] - 1,
+                                gene.shape[0], W_ih.ctypes.data, W_ho.ctypes.data, p(m_ih), p(v_ih), p(m_ho),
+                                p(v_ho), V, D, opt, {"sum": 0, "mean": 1}[reduce], lr, beta1, beta2, eps, t,
+                                loss.ctypes.data, nc.ctypes.data)
+    _capi.check(rc, "g2v_cbow_step_host")
+    return state, float(loss[0]), int(nc[0])

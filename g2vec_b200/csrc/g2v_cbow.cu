@@ -1,0 +1,424 @@
+// g2v_cbow.cu -- HOT PATH 2: modified CBOW (G2Vec.py:217-286) as fused sm_100a kernels.
+//
+// The reference builds  H = X.W_ih ; O = H.W_ho ; cost = mean(sigmoid_BCE(O, Y))  on a dense
+// multi-hot X [N, V] (99.7 % zeros) and lets TF1 autodiff + ApplyAdam train W_ih, W_ho
+// (G2Vec.py:239-246).  Here X is CSR (window -> gene ids) and one warp owns one window:
+//
+//   cbow_rows_kernel<VEC, BACKWARD>      D = 128*VEC, each lane owns VEC float4 of the row
+//     gather   h   = sum_{g in window} W_ih[g, :]          (512*VEC B coalesced per row, 8 rows in flight)
+//     logit    o   = <h, W_ho>                            (warp shuffle reduction)
+//     loss/acc     max(o,0) - o*y + log1p(exp(-|o|)),  (o > 0) == y
+//     grad     dO  = (sigmoid(o) - y) / N                 (N known up front: no global barrier)
+//     scatter  g_ih[g, :] += dO * W_ho  for g in window   (red.global.add.v4.f32, 16 B per lane)
+//              g_ho       += h * dO                       (registers -> smem -> one atomic per CTA)
+//   cbow_update_kernel                    dense epilogue over [V*D] (+[D]): TF1 Adam or SGD,
+//                                         float4, zeroes the gradient for the next step
+//
+// No tensor cores: the 128..512-wide reduction is a memory-bound gather/scatter, not a dense
+// contraction.  Algorithmic bytes per window: l*(8D+4)+5, per step + 32*V*D (Adam).
+#include "g2v_common.cuh"
+
+namespace g2v {
+
+constexpr int kCbowWarps = 8;
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+__device__ __forceinline__ void red_add4(float *p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ float sigmoid_stable(float x) {
+    if (x >= 0.f) { const float z = expf(-x); return 1.f / (1.f + z); }
+    const float z = expf(x);
+    return z / (1.f + z);
+}
+
+struct CtaAcc {   // per-CTA accumulators in shared memory
+    double loss;
+    unsigned long long correct;
+};
+
+template <int VEC, bool BACKWARD>
+__global__ void __launch_bounds__(kCbowWarps * 32)
+cbow_rows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ gene,
+                 const uint8_t *__restrict__ label, const int32_t *__restrict__ win,
+                 int64_t win_begin, int64_t n_win, float inv_n, const float *__restrict__ W_ih,
+                 const float *__restrict__ W_ho, float *__restrict__ g_ih, float *__restrict__ g_ho,
+                 double *__restrict__ loss_sum, unsigned long long *__restrict__ n_correct,
+                 int32_t reduce_mean) {
+    constexpr int D = 128 * VEC;
+    constexpr int D4 = D / 4;
+    constexpr int UNR = 8 / VEC;                 // 8 float4 (128 B) in flight per lane
+    __shared__ float sh_gho[BACKWARD ? D : 1];
+    __shared__ CtaAcc sh_acc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (BACKWARD) for (int i = threadIdx.x; i < D; i += blockDim.x) sh_gho[i] = 0.f;
+    if (threadIdx.x == 0) { sh_acc.loss = 0.0; sh_acc.correct = 0ull; }
+    __syncthreads();
+
+    const float4 *__restrict__ W4 = reinterpret_cast<const float4 *>(W_ih);
+    float4 who[VEC], gho[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        who[v] = ldg4(reinterpret_cast<const float4 *>(W_ho) + v * 32 + lane);
+        gho[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float loss_acc = 0.f;
+    unsigned correct_acc = 0;
+
+    const int64_t warps_total = (int64_t)gridDim.x * kCbowWarps;
+    for (int64_t i = (int64_t)blockIdx.x * kCbowWarps + warp; i < n_win; i += warps_total) {
+        const int64_t n = win ? (int64_t)__ldg(win + win_begin + i) : win_begin + i;
+        const int32_t b = __ldg(rowptr + n), e = __ldg(rowptr + n + 1);
+        const float y = (float)__ldg(label + n);
+        float4 h[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) h[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        // ---- gather + segmented sum
+        for (int32_t base = b; base < e; base += 32) {
+            const int cnt = min(32, e - base);
+            const int32_t g = (lane < cnt) ? __ldg(gene + base + lane) : 0;
+            for (int k = 0; k < cnt; k += UNR) {
+                float4 r[UNR][VEC];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int32_t gk = __shfl_sync(0xffffffffu, g, (k + u) & 31);
+                    const float4 *row = W4 + (size_t)gk * D4 + lane;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        r[u][v] = (k + u < cnt) ? ldg4(row + v * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        h[v].x += r[u][v].x; h[v].y += r[u][v].y; h[v].z += r[u][v].z; h[v].w += r[u][v].w;
+                    }
+            }
+        }
+        const float scale = (reduce_mean && e > b) ? 1.f / (float)(e - b) : 1.f;
+        float part = 0.f;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            if (reduce_mean) { h[v].x *= scale; h[v].y *= scale; h[v].z *= scale; h[v].w *= scale; }
+            part += h[v].x * who[v].x + h[v].y * who[v].y + h[v].z * who[v].z + h[v].w * who[v].w;
+        }
+        const float o = warp_sum(part);
+        if (lane == 0) {
+            correct_acc += ((o > 0.f) == (y != 0.f)) ? 1u : 0u;
+            if (BACKWARD) loss_acc += fmaxf(o, 0.f) - o * y + log1pf(expf(-fabsf(o)));
+        }
+        if (BACKWARD) {
+            const float dO = (sigmoid_stable(o) - y) * inv_n;
+            float4 gv[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                gho[v].x += h[v].x * dO; gho[v].y += h[v].y * dO; gho[v].z += h[v].z * dO; gho[v].w += h[v].w * dO;
+                const float s = dO * scale;
+                gv[v] = make_float4(who[v].x * s, who[v].y * s, who[v].z * s, who[v].w * s);
+            }
+            // ---- scatter-add the gradient rows
+            for (int32_t base = b; base < e; base += 32) {
+                const int cnt = min(32, e - base);
+                const int32_t g = (lane < cnt) ? __ldg(gene + base + lane) : 0;
+                for (int k = 0; k < cnt; ++k) {
+                    const int32_t gk = __shfl_sync(0xffffffffu, g, k);
+                    float *dst = g_ih + (size_t)gk * D + lane * 4;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) red_add4(dst + v * 128, gv[v]);
+                }
+            }
+        }
+    }
+
+    // ---- CTA-level reduction of g_ho / loss / correct, then one global atomic each
+    if (BACKWARD) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float *p = sh_gho + (v * 32 + lane) * 4;
+            atomicAdd(p + 0, gho[v].x); atomicAdd(p + 1, gho[v].y);
+            atomicAdd(p + 2, gho[v].z); atomicAdd(p + 3, gho[v].w);
+        }
+    }
+    if (lane == 0) {
+        if (BACKWARD) atomicAdd(&sh_acc.loss, (double)loss_acc);
+        atomicAdd(&sh_acc.correct, (unsigned long long)correct_acc);
+    }
+    __syncthreads();
+    if (BACKWARD) for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(g_ho + i, sh_gho[i]);
+    if (threadIdx.x == 0) {
+        if (BACKWARD && loss_sum) atomicAdd(loss_sum, sh_acc.loss);
+        if (n_correct) atomicAdd(n_correct, sh_acc.correct);
+    }
+}
+
+// Any D (not a multiple of 128): h and the g_ho partial live in shared memory per warp.
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kCbowWarps * 32)
+cbow_rows_generic_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ gene,
+                         const uint8_t *__restrict__ label, const int32_t *__restrict__ win,
+                         int64_t win_begin, int64_t n_win, float inv_n, const float *__restrict__ W_ih,
+                         const float *__restrict__ W_ho, float *__restrict__ g_ih,
+                         float *__restrict__ g_ho, double *__restrict__ loss_sum,
+                         unsigned long long *__restrict__ n_correct, int32_t D, int32_t reduce_mean) {
+    extern __shared__ float shf[];
+    __shared__ CtaAcc sh_acc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *h = shf + (size_t)warp * 2 * D;
+    float *gho = h + D;
+    for (int d = lane; d < D; d += 32) gho[d] = 0.f;
+    if (threadIdx.x == 0) { sh_acc.loss = 0.0; sh_acc.correct = 0ull; }
+    __syncthreads();
+    float loss_acc = 0.f;
+    unsigned correct_acc = 0;
+    const int64_t warps_total = (int64_t)gridDim.x * kCbowWarps;
+    for (int64_t i = (int64_t)blockIdx.x * kCbowWarps + warp; i < n_win; i += warps_total) {
+        const int64_t n = win ? (int64_t)__ldg(win + win_begin + i) : win_begin + i;
+        const int32_t b = __ldg(rowptr + n), e = __ldg(rowptr + n + 1);
+        const float y = (float)__ldg(label + n);
+        for (int d = lane; d < D; d += 32) h[d] = 0.f;
+        for (int32_t j = b; j < e; ++j) {
+            const float *row = W_ih + (size_t)__ldg(gene + j) * D;
+            for (int d = lane; d < D; d += 32) h[d] += __ldg(row + d);
+        }
+        const float scale = (reduce_mean && e > b) ? 1.f / (float)(e - b) : 1.f;
+        float part = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            if (reduce_mean) h[d] *= scale;
+            part += h[d] * __ldg(W_ho + d);
+        }
+        const float o = warp_sum(part);
+        if (lane == 0) {
+            correct_acc += ((o > 0.f) == (y != 0.f)) ? 1u : 0u;
+            if (BACKWARD) loss_acc += fmaxf(o, 0.f) - o * y + log1pf(expf(-fabsf(o)));
+        }
+        if (BACKWARD) {
+            const float dO = (sigmoid_stable(o) - y) * inv_n;
+            for (int d = lane; d < D; d += 32) gho[d] += h[d] * dO;
+            const float s = dO * scale;
+            for (int32_t j = b; j < e; ++j) {
+                float *dst = g_ih + (size_t)__ldg(gene + j) * D;
+                for (int d = lane; d < D; d += 32) atomicAdd(dst + d, __ldg(W_ho + d) * s);
+            }
+        }
+    }
+    if (BACKWARD) for (int d = lane; d < D; d += 32) atomicAdd(g_ho + d, gho[d]);
+    if (lane == 0) {
+        if (BACKWARD) atomicAdd(&sh_acc.loss, (double)loss_acc);
+        atomicAdd(&sh_acc.correct, (unsigned long long)correct_acc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (BACKWARD && loss_sum) atomicAdd(loss_sum, sh_acc.loss);
+        if (n_correct) atomicAdd(n_correct, sh_acc.correct);
+    }
+}
+
+// ---- optimizer epilogue --------------------------------------------------------------------
+// TF1 ApplyAdam (tensorflow/core/kernels/training_ops.cc):  m += (g-m)(1-b1); v += (g*g-v)(1-b2);
+// var -= (m*alpha)/(sqrt(v)+eps), alpha = lr*sqrt(1-b2^t)/(1-b1^t).
+__device__ __forceinline__ void adam1(float &w, float &m, float &v, float g, float alpha, float omb1,
+                                      float omb2, float eps) {
+    m += (g - m) * omb1;
+    v += (g * g - v) * omb2;
+    w -= (m * alpha) / (sqrtf(v) + eps);
+}
+
+template <int OPT>
+__global__ void __launch_bounds__(256)
+cbow_update_kernel(float *__restrict__ W, float *__restrict__ M, float *__restrict__ Vv,
+                   float *__restrict__ G, int64_t n, float *__restrict__ W2, float *__restrict__ M2,
+                   float *__restrict__ V2, float *__restrict__ G2, int64_t n2, float alpha, float omb1,
+                   float omb2, float eps) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n >> 2;
+    float4 *W4 = reinterpret_cast<float4 *>(W), *G4 = reinterpret_cast<float4 *>(G);
+    float4 *M4 = reinterpret_cast<float4 *>(M), *V4 = reinterpret_cast<float4 *>(Vv);
+    for (int64_t i = tid; i < n4; i += nthreads) {
+        float4 w = W4[i];
+        const float4 g = G4[i];
+        if (OPT == G2V_OPT_ADAM_TF1) {
+            float4 m = M4[i], v = V4[i];
+            adam1(w.x, m.x, v.x, g.x, alpha, omb1, omb2, eps);
+            adam1(w.y, m.y, v.y, g.y, alpha, omb1, omb2, eps);
+            adam1(w.z, m.z, v.z, g.z, alpha, omb1, omb2, eps);
+            adam1(w.w, m.w, v.w, g.w, alpha, omb1, omb2, eps);
+            M4[i] = m; V4[i] = v;
+        } else {
+            w.x -= alpha * g.x; w.y -= alpha * g.y; w.z -= alpha * g.z; w.w -= alpha * g.w;
+        }
+        W4[i] = w;
+        G4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // scalar tail of W_ih, then the [D] output layer
+    for (int64_t i = (n4 << 2) + tid; i < n + n2; i += nthreads) {
+        float *w, *m, *v, *g;
+        if (i < n) { w = W + i; m = M + i; v = Vv + i; g = G + i; }
+        else { const int64_t j = i - n; w = W2 + j; m = M2 + j; v = V2 + j; g = G2 + j; }
+        if (OPT == G2V_OPT_ADAM_TF1) adam1(*w, *m, *v, *g, alpha, omb1, omb2, eps);
+        else *w -= alpha * *g;
+        *g = 0.f;
+    }
+}
+
+static int rows_grid(const void *kernel, size_t smem, int64_t n_win, int *grid_out) {
+    DeviceProps dp;
+    if (device_props(&dp)) return 1;
+    if (dp.cc_major != 10) { set_error("needs an sm_100 device (found sm_%d%d); no CPU fallback", dp.cc_major, dp.cc_minor); return 2; }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kCbowWarps * 32, smem);
+    if (e != cudaSuccess || per_sm <= 0) { set_error("occupancy query failed: %s", cudaGetErrorString(e)); return 1; }
+    int64_t grid = (int64_t)dp.sm_count * per_sm;
+    const int64_t need = (n_win + kCbowWarps - 1) / kCbowWarps;
+    if (grid > need) grid = need;
+    *grid_out = (int)(grid > 0 ? grid : 1);
+    return 0;
+}
+
+template <bool BACKWARD>
+static int launch_rows(const int32_t *rowptr, const int32_t *gene, const uint8_t *label, const int32_t *win,
+                       int64_t win_begin, int64_t n_win, float inv_n, const float *W_ih, const float *W_ho,
+                       float *g_ih, float *g_ho, double *loss_sum, int64_t *n_correct, int32_t D,
+                       int32_t reduce, cudaStream_t st) {
+    unsigned long long *nc = reinterpret_cast<unsigned long long *>(n_correct);
+    int grid = 0, rc;
+#define G2V_LAUNCH_VEC(VEC)                                                                          \
+    {                                                                                                \
+        if ((rc = rows_grid((const void *)cbow_rows_kernel<VEC, BACKWARD>, 0, n_win, &grid))) return rc; \
+        cbow_rows_kernel<VEC, BACKWARD><<<grid, kCbowWarps * 32, 0, st>>>(                           \
+            rowptr, gene, label, win, win_begin, n_win, inv_n, W_ih, W_ho, g_ih, g_ho, loss_sum, nc, reduce); \
+    }
+    if (D == 128) G2V_LAUNCH_VEC(1)
+    else if (D == 256) G2V_LAUNCH_VEC(2)
+    else if (D == 512) G2V_LAUNCH_VEC(4)
+    else {
+        const size_t smem = (size_t)kCbowWarps * 2 * D * sizeof(float);
+        DeviceProps dp;
+        if (device_props(&dp)) return 1;
+        G2V_REQUIRE(smem <= (size_t)dp.max_smem_optin, "sizeHiddenlayer %d too large for the generic kernel", D);
+        G2V_CUDA_OK(cudaFuncSetAttribute(cbow_rows_generic_kernel<BACKWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if ((rc = rows_grid((const void *)cbow_rows_generic_kernel<BACKWARD>, smem, n_win, &grid))) return rc;
+        cbow_rows_generic_kernel<BACKWARD><<<grid, kCbowWarps * 32, smem, st>>>(
+            rowptr, gene, label, win, win_begin, n_win, inv_n, W_ih, W_ho, g_ih, g_ho, loss_sum, nc, D, reduce);
+    }
+#undef G2V_LAUNCH_VEC
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace g2v
+
+using namespace g2v;
+
+extern "C" int g2v_cbow_fwdbwd(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
+                               const int32_t *win, int64_t win_begin, int64_t n_win, float inv_n_total,
+                               const float *W_ih, const float *W_ho, float *g_ih, float *g_ho,
+                               double *loss_sum, int64_t *n_correct, int32_t V, int32_t D, int32_t reduce,
+                               void *stream) {
+    G2V_REQUIRE(V > 0 && D > 0 && n_win >= 0 && win_begin >= 0, "g2v_cbow_fwdbwd: bad sizes (V=%d D=%d n_win=%lld)", V, D, (long long)n_win);
+    G2V_REQUIRE(rowptr && label && W_ih && W_ho && g_ih && g_ho, "g2v_cbow_fwdbwd: null pointer");
+    G2V_REQUIRE(reduce == G2V_REDUCE_SUM || reduce == G2V_REDUCE_MEAN, "g2v_cbow_fwdbwd: unknown reduce %d", reduce);
+    if (n_win == 0) return 0;
+    return launch_rows<true>(rowptr, gene, label, win, win_begin, n_win, inv_n_total, W_ih, W_ho, g_ih, g_ho,
+                             loss_sum, n_correct, D, reduce, (cudaStream_t)stream);
+}
+
+extern "C" int g2v_cbow_eval(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
+                             const int32_t *win, int64_t win_begin, int64_t n_win, const float *W_ih,
+                             const float *W_ho, int64_t *n_correct, int32_t V, int32_t D, int32_t reduce,
+                             void *stream) {
+    G2V_REQUIRE(V > 0 && D > 0 && n_win >= 0 && win_begin >= 0, "g2v_cbow_eval: bad sizes");
+    G2V_REQUIRE(rowptr && label && W_ih && W_ho && n_correct, "g2v_cbow_eval: null pointer");
+    G2V_REQUIRE(reduce == G2V_REDUCE_SUM || reduce == G2V_REDUCE_MEAN, "g2v_cbow_eval: unknown reduce %d", reduce);
+    if (n_win == 0) return 0;
+    return launch_rows<false>(rowptr, gene, label, win, win_begin, n_win, 0.f, W_ih, W_ho, nullptr, nullptr,
+                              nullptr, n_correct, D, reduce, (cudaStream_t)stream);
+}
+
+extern "C" int g2v_cbow_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
+                               float *g_ih, float *g_ho, int32_t V, int32_t D, int32_t optimizer, float lr,
+                               float beta1, float beta2, float eps, int32_t t, void *stream) {
+    G2V_REQUIRE(V > 0 && D > 0 && t >= 1, "g2v_cbow_update: bad sizes (V=%d D=%d t=%d)", V, D, t);
+    G2V_REQUIRE(W_ih && W_ho && g_ih && g_ho, "g2v_cbow_update: null pointer");
+    G2V_REQUIRE(optimizer == G2V_OPT_ADAM_TF1 || optimizer == G2V_OPT_SGD, "g2v_cbow_update: unknown optimizer %d", optimizer);
+    G2V_REQUIRE(optimizer == G2V_OPT_SGD || (m_ih && v_ih && m_ho && v_ho), "g2v_cbow_update: Adam needs m/v buffers");
+    DeviceProps dp;
+    if (device_props(&dp)) return 1;
+    const int64_t n = (int64_t)V * D;
+    int64_t blocks = (n / 4 + 255) / 256;
+    const int64_t cap = (int64_t)dp.sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (optimizer == G2V_OPT_ADAM_TF1) {
+        // beta^t by repeated float32 multiplication, as TF1's beta1_power / beta2_power variables
+        float b1p = 1.f, b2p = 1.f;
+        for (int i = 0; i < t; ++i) { b1p *= beta1; b2p *= beta2; }
+        const float alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+        cbow_update_kernel<G2V_OPT_ADAM_TF1><<<(unsigned)blocks, 256, 0, st>>>(
+            W_ih, m_ih, v_ih, g_ih, n, W_ho, m_ho, v_ho, g_ho, (int64_t)D, alpha, 1.f - beta1, 1.f - beta2, eps);
+    } else {
+        cbow_update_kernel<G2V_OPT_SGD><<<(unsigned)blocks, 256, 0, st>>>(
+            W_ih, nullptr, nullptr, g_ih, n, W_ho, nullptr, nullptr, g_ho, (int64_t)D, lr, 0.f, 0.f, 0.f);
+    }
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int g2v_cbow_step_host(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
+                                  int64_t n_win, int64_t nnz, float *W_ih, float *W_ho, float *m_ih,
+                                  float *v_ih, float *m_ho, float *v_ho, int32_t V, int32_t D,
+                                  int32_t optimizer, int32_t reduce, float lr, float beta1, float beta2,
+                                  float eps, int32_t t, double *loss_sum, int64_t *n_correct) {
+    G2V_REQUIRE(V > 0 && D > 0 && n_win > 0 && nnz >= 0, "g2v_cbow_step_host: bad sizes");
+    G2V_REQUIRE(optimizer == G2V_OPT_SGD || (m_ih && v_ih && m_ho && v_ho), "g2v_cbow_step_host: Adam needs m/v");
+    const size_t nW = (size_t)V * D * sizeof(float), nD = (size_t)D * sizeof(float);
+    const bool adam = optimizer == G2V_OPT_ADAM_TF1;
+    // one slab: rowptr | gene | label | W | Wo | m | v | mo | vo | g | go | loss | correct
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_rp = take(sizeof(int32_t) * (size_t)(n_win + 1)), o_ge = take(sizeof(int32_t) * (size_t)(nnz ? nnz : 1)),
+                 o_la = take((size_t)n_win), o_W = take(nW), o_Wo = take(nD), o_m = take(nW), o_v = take(nW),
+                 o_mo = take(nD), o_vo = take(nD), o_g = take(nW), o_go = take(nD), o_ls = take(8), o_nc = take(8);
+    char *d = nullptr;
+    cudaStream_t st = nullptr;
+    int rc = 1;
+    do {
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) break;
+        if (cudaMalloc(&d, off) != cudaSuccess) break;
+#define H2D(dst, src, bytes) if (cudaMemcpyAsync(d + (dst), (src), (bytes), cudaMemcpyHostToDevice, st) != cudaSuccess) break
+#define D2H(dst, src, bytes) if (cudaMemcpyAsync((dst), d + (src), (bytes), cudaMemcpyDeviceToHost, st) != cudaSuccess) break
+        H2D(o_rp, rowptr, sizeof(int32_t) * (size_t)(n_win + 1));
+        if (nnz) { H2D(o_ge, gene, sizeof(int32_t) * (size_t)nnz); }
+        H2D(o_la, label, (size_t)n_win);
+        H2D(o_W, W_ih, nW); H2D(o_Wo, W_ho, nD);
+        if (adam) { H2D(o_m, m_ih, nW); H2D(o_v, v_ih, nW); H2D(o_mo, m_ho, nD); H2D(o_vo, v_ho, nD); }
+        if (cudaMemsetAsync(d + o_g, 0, off - o_g, st) != cudaSuccess) break;
+        rc = g2v_cbow_fwdbwd((int32_t *)(d + o_rp), (int32_t *)(d + o_ge), (uint8_t *)(d + o_la), nullptr, 0, n_win,
+                             1.0f / (float)n_win, (float *)(d + o_W), (float *)(d + o_Wo), (float *)(d + o_g),
+                             (float *)(d + o_go), (double *)(d + o_ls), (int64_t *)(d + o_nc), V, D, reduce, st);
+        if (rc) break;
+        rc = g2v_cbow_update((float *)(d + o_W), (float *)(d + o_Wo), (float *)(d + o_m), (float *)(d + o_v),
+                             (float *)(d + o_mo), (float *)(d + o_vo), (float *)(d + o_g), (float *)(d + o_go), V, D,
+                             optimizer, lr, beta1, beta2, eps, t, st);
+        if (rc) break;
+        rc = 1;
+        D2H(W_ih, o_W, nW); D2H(W_ho, o_Wo, nD);
+        if (adam) { D2H(m_ih, o_m, nW); D2H(v_ih, o_v, nW); D2H(m_ho, o_mo, nD); D2H(v_ho, o_vo, nD); }
+        if (loss_sum) { D2H(loss_sum, o_ls, 8); }
+        if (n_correct) { D2H(n_correct, o_nc, 8); }
+#undef H2D
+#undef D2H
+        if (cudaStreamSynchronize(st) != cudaSuccess) break;
+        rc = 0;
+    } while (0);
+    if (rc == 1) set_error("g2v_cbow_step_host: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}

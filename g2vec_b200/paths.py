@@ -1,0 +1,89 @@
+"""Glue between the two hot paths: canonicalise walks, de-duplicate, drop paths
+common to both groups, emit CSR context windows, and the gene-frequency vote.
+
+Reference: ``tuple(sorted(path))`` into a set (G2Vec.py:345,351), ``integrate_pathSet``
+(:310-322, dense int32 [n_paths, n_genes+1]) and ``count_geneFreq`` (:288-308).  Here paths stay on
+the device as padded sorted rows and the dense multi-hot matrix (1.37 GB at ex_* scale) is never
+built: the trainer consumes CSR windows.  torch sort/unique are used as plumbing.
+"""
+import numpy as np
+import torch
+
+PAD = 2**31 - 1
+
+
+def canonical_rows(nodes, lens=None):
+    """Walk rows (visit order, -1 padded) -> unique rows, each sorted ascending, PAD-padded;
+    rows themselves in lexicographic order (the set of G2Vec.py:351)."""
+    rows = torch.where(nodes < 0, torch.full_like(nodes, PAD), nodes)
+    rows, _ = torch.sort(rows, dim=1)
+    return torch.unique(rows, dim=0)
+
+
+def integrate(rows_good, rows_poor):
+    """integrate_pathSet (G2Vec.py:310-322): remove paths present in both groups, label the rest
+    (0 = good, 1 = poor).  Returns (rows [N, L] PAD-padded, labels uint8 [N]); good rows first."""
+    L = max(rows_good.shape[1], rows_poor.shape[1])
+
+    def widen(r):
+        if r.shape[1] == L:
+            return r
+        pad = torch.full((r.shape[0], L - r.shape[1]), PAD, dtype=r.dtype, device=r.device)
+        return torch.cat([r, pad], dim=1)
+
+    a, b = widen(rows_good), widen(rows_poor)
+    both = torch.cat([a, b], dim=0)
+    lab = torch.cat([torch.zeros(a.shape[0], dtype=torch.uint8, device=a.device),
+                     torch.ones(b.shape[0], dtype=torch.uint8, device=b.device)])
+    _, inv, cnt = torch.unique(both, dim=0, return_inverse=True, return_counts=True)
+    keep = cnt[inv] == 1                       # each group's rows are already unique
+    return both[keep], lab[keep]
+
+
+def windows_csr(rows, labels):
+    """Padded sorted rows -> CSR windows (rowptr int32 [N+1], gene int32 [nnz], label uint8 [N])."""
+    valid = rows != PAD
+    lens = valid.sum(dim=1)
+    rowptr = torch.zeros(rows.shape[0] + 1, dtype=torch.int64, device=rows.device)
+    rowptr[1:] = torch.cumsum(lens, dim=0)
+    if int(rowptr[-1]) >= 2**31:
+        raise ValueError("too many window entries for int32 CSR")
+    gene = rows[valid].to(torch.int32)
+    return rowptr.to(torch.int32), gene, labels.to(torch.uint8)
+
+
+def gene_freq_codes(rowptr, gene, labels, n_genes):
+    """count_geneFreq (G2Vec.py:288-308) as a vector: code[g] = 0 (more good paths), 1 (more poor),
+    2 (tie), -1 (gene in no path).  The reference returns a dict over the genes that occur."""
+    lens = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
+    lab = torch.repeat_interleave(labels.to(torch.int64), lens)
+    g = gene.to(torch.int64)
+    fp = torch.bincount(g, weights=lab.to(torch.float64), minlength=n_genes)
+    tot = torch.bincount(g, minlength=n_genes).to(torch.float64)
+    fg = tot - fp
+    code = torch.full((n_genes,), -1, dtype=torch.int64, device=gene.device)
+    code[(tot > 0) & (fg > fp)] = 0
+    code[(tot > 0) & (fg < fp)] = 1
+    code[(tot > 0) & (fg == fp)] = 2
+    return code
+
+
+def gene_freq_dict(code, gene_names):
+    code = code.cpu().numpy()
+    return {gene_names[i]: int(c) for i, c in enumerate(code) if c >= 0}
+
+
+def rows_to_set(rows):
+    """Padded rows -> python set of tuples (for the reference-shaped adapters and the tests)."""
+    r = rows.cpu().numpy()
+    return {tuple(int(x) for x in row[row != PAD]) for row in r}
+
+
+def dense_pathlist_to_csr(pathList):
+    """The reference's dense pathList [N, n_genes+1] (last column = label) -> CSR windows (NumPy)."""
+    P = np.asarray(pathList)
+    X = P[:, :-1]
+    r, c = np.nonzero(X)
+    rowptr = np.zeros(P.shape[0] + 1, dtype=np.int64)
+    np.add.at(rowptr, r + 1, 1)
+    return np.cumsum(rowptr).astype(np.int32), c.astype(np.int32), P[:, -1].astype(np.uint8)

@@ -1,0 +1,108 @@
+"""HOT PATH 1, host side: the walk sampler behind the reference's call
+``generate_pathSet(adjMat, args.lenPath, args.numRepetition)`` (/root/reference/G2Vec.py:62,
+324-352).  The work is done by ``g2v_walk_launch`` (csrc/g2v_walk.cu) on the current CUDA
+device; this module only owns buffers (torch tensors) and the walker-range bookkeeping.
+"""
+import numpy as np
+import torch
+
+from . import _capi, graph as _graph
+
+
+def _dev(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("g2vec_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _to_dev(a, dtype, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype).contiguous()
+    a = np.ascontiguousarray(a)
+    if dtype == torch.int32 and a.dtype == np.uint32:
+        a = a.view(np.int32)           # same bits; the kernel reads uint32
+    return torch.from_numpy(a).to(device=device, dtype=dtype, non_blocking=True)
+
+
+class WalkGraph:
+    """One group's directed weighted graph resident in HBM as CSR
+    (rowptr int32 [V+1], col int32 [E] ascending per row, qw uint32 [E] stored as int32 bits)."""
+
+    def __init__(self, rowptr, col, weights=None, qw=None, device=None):
+        device = _dev(device)
+        if qw is None:
+            if weights is None:
+                raise ValueError("need weights or qw")
+            qw = _graph.quantise_weights(np.asarray(weights.cpu() if isinstance(weights, torch.Tensor) else weights))
+        self.rowptr = _to_dev(rowptr, torch.int32, device)
+        self.col = _to_dev(col, torch.int32, device)
+        self.qw = _to_dev(qw, torch.int32, device)
+        self.V = int(self.rowptr.shape[0]) - 1
+        self.E = int(self.col.shape[0])
+        if self.qw.shape[0] != self.E:
+            raise ValueError("col / weight length mismatch")
+        self.device = device
+        self._ws = torch.zeros(max(int(_capi.load().g2v_walk_workspace_bytes()), 8), dtype=torch.uint8, device=device)
+
+    @classmethod
+    def from_dense(cls, adjMat, device=None):
+        rp, col, w = _graph.csr_from_dense(adjMat)
+        return cls(rp, col, weights=w, device=device)
+
+    def nbytes(self):
+        return 4 * (self.V + 1) + 8 * self.E
+
+
+def num_walkers(V, reps, begin=0, end=None, stride=1):
+    end = V * reps if end is None else end
+    return max(0, (end - begin + stride - 1) // stride)
+
+
+def generate_paths(g, len_path, reps, seed=0, group=0, walker_begin=0, walker_end=None, walker_stride=1,
+                   out=None):
+    """Run walkers w = walker_begin + i*walker_stride < walker_end (w = rep*V + src) of graph ``g``.
+
+    Returns (nodes int32 [n, len_path] in VISIT order padded with -1, lens int32 [n]) as device
+    tensors; asynchronous on the current stream."""
+    lib = _capi.load()
+    end = g.V * reps if walker_end is None else walker_end
+    n = num_walkers(g.V, reps, walker_begin, end, walker_stride)
+    if out is None:
+        nodes = torch.empty((n, len_path), dtype=torch.int32, device=g.device)
+        lens = torch.empty((n,), dtype=torch.int32, device=g.device)
+    else:
+        nodes, lens = out
+        assert nodes.shape == (n, len_path) and lens.shape == (n,) and nodes.is_contiguous()
+    with torch.cuda.device(g.device):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = lib.g2v_walk_launch(g.rowptr.data_ptr(), g.col.data_ptr(), g.qw.data_ptr(), g.V, g.E, int(len_path),
+                                 int(seed) & (2**64 - 1), int(group), int(walker_begin), int(end),
+                                 int(walker_stride), nodes.data_ptr(), lens.data_ptr(), g._ws.data_ptr(), st)
+    _capi.check(rc, "g2v_walk_launch")
+    return nodes, lens
+
+
+def generate_paths_host(rowptr, col, qw, len_path, reps, seed=0, group=0, walker_begin=0, walker_end=None,
+                        walker_stride=1):
+    """Same through ``g2v_walk_host``: NumPy arrays in, NumPy arrays out (the C ABI does the copies)."""
+    lib = _capi.load()
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); col = np.ascontiguousarray(col, dtype=np.int32)
+    qw = np.ascontiguousarray(qw, dtype=np.uint32)
+    V = rowptr.shape[0] - 1
+    end = V * reps if walker_end is None else walker_end
+    n = num_walkers(V, reps, walker_begin, end, walker_stride)
+    nodes = np.empty((n, len_path), dtype=np.int32); lens = np.empty(n, dtype=np.int32)
+    rc = lib.g2v_walk_host(rowptr.ctypes.data, col.ctypes.data, qw.ctypes.data, V, col.shape[0], int(len_path),
+                           int(seed) & (2**64 - 1), int(group), int(walker_begin), int(end), int(walker_stride),
+                           nodes.ctypes.data, lens.ctypes.data)
+    _capi.check(rc, "g2v_walk_host")
+    return nodes, lens
+
+
+def generate_pathSet(adjMat, maximumLength, iterations, seed=0, group=0):
+    """Drop-in for the reference's ``generate_pathSet(adjMat, maximumLength, iterations)``
+    (G2Vec.py:324): dense adjacency (or a WalkGraph) in, ``set`` of sorted int tuples out."""
+    g = adjMat if isinstance(adjMat, WalkGraph) else WalkGraph.from_dense(adjMat)
+    nodes, lens = generate_paths(g, maximumLength, iterations, seed=seed, group=group)
+    nodes = nodes.cpu().numpy(); lens = lens.cpu().numpy()
+    return {tuple(sorted(int(x) for x in row[:n])) for row, n in zip(nodes, lens)}

@@ -1,0 +1,133 @@
+/*
+ * g2vec_b200.h -- C ABI of libg2vec_b200.so: the two G2Vec hot paths as sm_100a CUDA.
+ *
+ * The reference (mathcom/G2Vec) has no FFI or plugin interface: its boundary for these
+ * paths is two plain Python calls in main(),
+ *     pathSet = generate_pathSet(adjMat, args.lenPath, args.numRepetition)     G2Vec.py:62
+ *     genetovec['mat'] = compute_genetovec(pathList, n_genes, hidden, lr)      G2Vec.py:74
+ * The entry points below are what a binding for those two call sites needs; the ctypes
+ * binding that ships is g2vec_b200/_capi.py, and INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions, no torch types.
+ *   - every function returns 0 on success, non-zero on failure; g2v_last_error() then
+ *     returns a thread-local message.
+ *   - `stream` is a cudaStream_t passed as void*; device entry points are asynchronous on
+ *     it and never synchronise.  Buffers are owned by the caller.
+ *   - `_host` entry points take HOST pointers, do their own device allocation and
+ *     host<->device copies, and return after the result is back in host memory.
+ *   - there is no CPU fallback: without a usable sm_100 device the calls fail.
+ */
+#ifndef G2VEC_B200_H
+#define G2VEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2V_ABI_VERSION 1
+
+/* optimizer codes for g2v_cbow_update */
+#define G2V_OPT_ADAM_TF1 0 /* tf.train.AdamOptimizer, G2Vec.py:246 (parity default) */
+#define G2V_OPT_SGD 1      /* var -= lr * g (north_star variant) */
+
+/* context reduction for the CBOW forward */
+#define G2V_REDUCE_SUM 0  /* H = X.W_ih, G2Vec.py:239 (parity default) */
+#define G2V_REDUCE_MEAN 1 /* H = X.W_ih / len(window) */
+
+int g2v_abi_version(void);
+const char *g2v_last_error(void);
+
+/* Device facts (current device): SM count, compute capability, L2 bytes, and the number of
+ * kernels this library has launched since load (bench.py's gpu_launches). */
+int g2v_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *l2_bytes);
+int64_t g2v_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * HOT PATH 1 -- walk sampler.  Replaces generate_pathSet / generate_randomPath,
+ * G2Vec.py:324-352, for the walkers  w = walker_begin + i*walker_stride < walker_end,
+ * w = rep*V + src  (rep = G2Vec.py:348 `step`, src = :349).
+ *
+ *   rowptr [V+1], col [E] (ascending inside a row = dense row order), qw [E]: CSR of the
+ *     group's directed adjacency (rows = out-edges, G2Vec.py:390) with weights quantised to
+ *     integers, 1 <= qw <= 2^24  (q = rint(|PCC| * 2^16)).
+ *   L: --lenPath, the maximum number of NODES of a path (G2Vec.py:331).  1 <= L <= 4096.
+ *   seed/group: Philox4x32-10 key and the high bits of the walker's subsequence
+ *     (subsequence = group*2^40 + w, 64-bit draw s = words 2s,2s+1), so that any
+ *     (walker, step) is addressable independently: results do not depend on sharding.
+ *   out_nodes [n*L]: visit order of walker i in row i, padded with -1  (the reference
+ *     sorts afterwards, G2Vec.py:345).  out_len [n]: nodes visited.  n = number of walkers.
+ *   workspace: >= g2v_walk_workspace_bytes() bytes of device scratch (zeroed by the call).
+ * ------------------------------------------------------------------------------------- */
+size_t g2v_walk_workspace_bytes(void);
+int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const uint32_t *qw, int32_t V,
+                    int64_t E, int32_t L, uint64_t seed, uint32_t group, int64_t walker_begin,
+                    int64_t walker_end, int64_t walker_stride, int32_t *out_nodes,
+                    int32_t *out_len, void *workspace, void *stream);
+
+/* Same, HOST pointers in and out (allocates, copies, launches, copies back, frees). */
+int g2v_walk_host(const int32_t *rowptr, const int32_t *col, const uint32_t *qw, int32_t V,
+                  int64_t E, int32_t L, uint64_t seed, uint32_t group, int64_t walker_begin,
+                  int64_t walker_end, int64_t walker_stride, int32_t *out_nodes,
+                  int32_t *out_len);
+
+/* ---------------------------------------------------------------------------------------
+ * HOT PATH 2 -- modified CBOW.  Replaces the TF1 graph of compute_genetovec,
+ * G2Vec.py:231-251, one optimizer step at a time; the epoch loop and the early stop
+ * (G2Vec.py:262-283) stay with the host (g2vec_b200/cbow.py).
+ *
+ * Windows (the rows of pathList, G2Vec.py:316-320) are CSR: rowptr [N+1], gene [nnz],
+ * label [N] (0 good / 1 poor).  `win` (nullable) is a list of window indices (the shuffled
+ * 80/20 split of G2Vec.py:219-222); NULL means windows win_begin..win_begin+n_win-1.
+ * W_ih [V*D] row-major are the gene vectors; W_ho [D].
+ *
+ * g2v_cbow_fwdbwd: for every listed window, gather the rows of its genes, reduce (sum),
+ *   logit o = h.W_ho, dO = (sigmoid(o) - y) * inv_n_total, then ADD  dO*W_ho into
+ *   g_ih[gene,:] for each gene of the window and h*dO into g_ho.  Adds the BCE loss sum
+ *   into *loss_sum (double) and the count of (o > 0) == y into *n_correct.  g_ih, g_ho,
+ *   loss_sum, n_correct are ACCUMULATED (device memory; the caller or g2v_cbow_update zeroes).
+ * g2v_cbow_update: optimizer epilogue over W_ih and W_ho from g_ih / g_ho (after the
+ *   all-reduce when multi-GPU); zeroes g_ih / g_ho for the next step.  t = 1-based step.
+ * g2v_cbow_eval: forward only; adds the count of correct predictions into *n_correct.
+ * ------------------------------------------------------------------------------------- */
+int g2v_cbow_fwdbwd(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
+                    const int32_t *win, int64_t win_begin, int64_t n_win, float inv_n_total,
+                    const float *W_ih, const float *W_ho, float *g_ih, float *g_ho,
+                    double *loss_sum, int64_t *n_correct, int32_t V, int32_t D, int32_t reduce,
+                    void *stream);
+
+int g2v_cbow_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
+                    float *g_ih, float *g_ho, int32_t V, int32_t D, int32_t optimizer, float lr,
+                    float beta1, float beta2, float eps, int32_t t, void *stream);
+
+int g2v_cbow_eval(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
+                  const int32_t *win, int64_t win_begin, int64_t n_win, const float *W_ih,
+                  const float *W_ho, int64_t *n_correct, int32_t V, int32_t D, int32_t reduce,
+                  void *stream);
+
+/* One full-batch step from HOST buffers: uploads the windows and the parameters/optimizer
+ * state, runs fwdbwd + update, downloads the updated parameters/state, the loss sum and the
+ * correct count (of the pre-update forward).  m/v may be NULL for SGD. */
+int g2v_cbow_step_host(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
+                       int64_t n_win, int64_t nnz, float *W_ih, float *W_ho, float *m_ih,
+                       float *v_ih, float *m_ho, float *v_ho, int32_t V, int32_t D,
+                       int32_t optimizer, int32_t reduce, float lr, float beta1, float beta2,
+                       float eps, int32_t t, double *loss_sum, int64_t *n_correct);
+
+/* ---------------------------------------------------------------------------------------
+ * Test hooks (used by tests/ only): 64-bit draws 0..n-1 of one walker subsequence from the
+ * kernel's own Philox, and the same words from curand's Philox4_32_10 generator
+ * (curand_init(seed, subsequence, 0)), to prove the stream is curand-compatible.
+ * ------------------------------------------------------------------------------------- */
+int g2v_test_draws(uint64_t seed, uint64_t subsequence, int32_t n, uint64_t *out_dev, void *stream);
+int g2v_test_curand_draws(uint64_t seed, uint64_t subsequence, int32_t n, uint64_t *out_dev,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2VEC_B200_H */

@@ -195,7 +195,10 @@ int g2v_oracle_cbow_grad(const int32_t *rowptr, const int32_t *gene, const uint8
 void g2v_oracle_adam(float *var, float *m, float *v, const float *g, int64_t n,
                      float lr, float beta1, float beta2, float eps, int32_t t)
 {
-    float b1p = powf(beta1, (float)t), b2p = powf(beta2, (float)t);
+    /* TF1 keeps beta1_power / beta2_power as float32 variables multiplied once per step
+     * (AdamOptimizer._finish), i.e. beta^t by repeated float32 multiplication. */
+    float b1p = 1.f, b2p = 1.f;
+    for (int32_t i = 0; i < t; ++i) { b1p *= beta1; b2p *= beta2; }
     float alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
     for (int64_t i = 0; i < n; ++i) {
         m[i] += (g[i] - m[i]) * (1.f - beta1);
