@@ -49,8 +49,8 @@ def parse():
     p.add_argument("--optimizer", default="adam", choices=["adam", "sgd"])
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--cpu-sample-windows", type=int, default=8192)
-    p.add_argument("--cpu-sample-starts", type=int, default=400)
+    p.add_argument("--cpu-sample-windows", type=int, default=32768)
+    p.add_argument("--cpu-sample-starts", type=int, default=2000)
     return p.parse_args()
 
 
@@ -422,12 +422,12 @@ def cpu_cbow_setup(rowptr, gene, label, V, D, n_sample):
 def cpu_baseline(args, gs, V, D, L, rowptr, gene, label):
     model, data, n_tr, n_va, threads = cpu_cbow_setup(rowptr, gene, label, V, D, args.cpu_sample_windows)
     model.epoch(*data)
-    t0 = time.perf_counter(); n = 3
+    t0 = time.perf_counter(); n = 5
     for _ in range(n):
         model.epoch(*data)
     dt = (time.perf_counter() - t0) / n
     cpu = {"value": n_tr / dt, "unit": UNIT, "cores": threads, "kind": "port",
-           "sample": "%d training + %d validation windows (dense X [%d,%d] f32), 3 epochs of the reference's dense "
+           "sample": "%d training + %d validation windows (dense X [%d,%d] f32), 5 epochs of the reference's dense "
                      "formulation (oracle/dense_cbow.py, torch-CPU matmul); TensorFlow 1.x is not installable here"
                      % (n_tr, n_va, n_tr, V), "ms_per_step": dt * 1e3}
     rate, visits, wdt = cpu_walk_rate(gs, L, args.cpu_sample_starts, 1)
@@ -459,7 +459,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / K
     value = n_tr / dt
     cores = os.cpu_count() or 1
-    rate, visits, wdt = cpu_walk_rate(gs, L, max(args.cpu_sample_starts, 4 * cores), cores)
+    rate, visits, wdt = cpu_walk_rate(gs, L, max(args.cpu_sample_starts, 100 * cores), cores)
     sample = ("each step = one epoch (G2Vec.py:262-267) of the dense formulation on %d training + %d validation "
               "windows of the workload (dense X [%d,%d] f32)" % (n_tr, n_va, n_tr, V))
     line = {

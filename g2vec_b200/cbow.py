@@ -136,7 +136,8 @@ def _dist():
 
 
 def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500, seed=0, optimizer="adam",
-               reduce="sum", W_ih0=None, W_ho0=None, split=None, early_stop=True, log=print, return_info=False):
+               reduce="sum", W_ih0=None, W_ho0=None, split=None, early_stop=True, log=print, return_info=False,
+               eval_train="lazy"):
     """Train the modified CBOW on CSR windows and return W_ih (np.float32 [n_genes, hidden]) exactly as
     ``compute_genetovec`` does: the weights after the last step whose validation accuracy did not drop.
 
@@ -166,24 +167,34 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
     before_val, before_tr = np.float32(-1.0), np.float32(0.0)
     result = model.W_ih.clone()
     hist, stop = [], None
+    f32 = np.float32
     for step in range(max_epoch):
         model.acc.zero_()
         if len(tr_loc):
-            model.fwdbwd(tr_d, n_tr)
+            model.fwdbwd(tr_d, n_tr)          # acc[1] += correct predictions with the PRE-update weights
         if dist:
             dist.all_reduce(model.g_ih)
             dist.all_reduce(model.g_ho)
         model.update()
         if len(va_loc):
             model.evaluate(va_d, 2)
-        if len(tr_loc):
+        # ACC[tr] of G2Vec.py:267 uses the post-update weights, i.e. exactly what the NEXT step's training
+        # forward computes.  It is only printed every 5th step and at the stop, so the extra
+        # forward pass is run only when its value is shown now; otherwise it arrives one step later for free.
+        show = (step % 5 == 0 and log is not None) or step == max_epoch - 1 or eval_train == "always"
+        if show and len(tr_loc):
             model.evaluate(tr_d, 3)
         if dist:
-            dist.all_reduce(model.acc[2:4])
+            dist.all_reduce(model.acc[1:4])
         acc = model.acc.cpu()                                   # the step's only host sync
-        acc_val = np.float32(int(acc[2])) / np.float32(max(n_va, 1))
-        acc_tr = np.float32(int(acc[3])) / np.float32(max(n_tr, 1))
-        hist.append((step, float(acc_val), float(acc_tr)))
+        acc_val = f32(int(acc[2])) / f32(max(n_va, 1))
+        acc_tr_prev = f32(int(acc[1])) / f32(max(n_tr, 1))      # = ACC[tr] of step-1
+        acc_tr = f32(int(acc[3])) / f32(max(n_tr, 1)) if show else None
+        if hist and hist[-1][2] is None:
+            hist[-1] = (hist[-1][0], hist[-1][1], float(acc_tr_prev))
+        if step > 0:
+            before_tr = acc_tr_prev
+        hist.append((step, float(acc_val), None if acc_tr is None else float(acc_tr)))
         if step % 5 == 0 and log:
             t1 = time.time()
             log("    - Epoch: %03d\tACC[val]=%.4f\tACC[tr]=%.4f (%.3f sec)" % (step, acc_val, acc_tr, t1 - t0))
@@ -194,7 +205,7 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
                     % (step - 1, before_val, before_tr, time.time() - t0))
             stop = step
             break
-        before_val, before_tr = acc_val, acc_tr
+        before_val = acc_val
         result.copy_(model.W_ih)
     if log:
         log("    Optimization Finish")

@@ -1,0 +1,39 @@
+"""torchrun worker for tests/test_gpu_multi.py: N-GPU run of both hot paths, rank 0 saves the results."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main(out):
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import g2vec_b200 as g2v
+    from tests import helpers
+    # walks: interleaved shards, gathered on rank 0
+    rp, col, w = helpers.ex_graph(1)
+    g = g2v.WalkGraph(rp, col, weights=w)
+    nodes, lens = g2v.generate_paths(g, 80, 2, seed=7, group=1, walker_begin=rank, walker_stride=world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (nodes.cpu().numpy(), lens.cpu().numpy()))
+    # CBOW: 5 steps on the oracle-made ex_* windows
+    (rowptr, gene, label), _ = helpers.ex_windows(reps=2)
+    W0, Wo0 = helpers.init_weights(7523, 128, 0)
+    got, info = g2v.train_cbow(rowptr, gene, label, 7523, 128, 0.005, max_epoch=5, seed=0, W_ih0=W0, W_ho0=Wo0,
+                               early_stop=False, log=None, return_info=True)
+    if rank == 0:
+        full = np.empty((2 * 7523, 80), np.int32); fl = np.empty(2 * 7523, np.int32)
+        for r in range(world):
+            full[r::world], fl[r::world] = gathered[r]
+        np.savez(out, W=got, hist=np.array(info["history"], dtype=np.float64), nodes=full, lens=fl)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -1,0 +1,40 @@
+"""N-GPU == 1-GPU (needs >= 2 GPUs; run with `gpurun --gpus 2 -- python -m pytest tests -m gpu`).
+Walks: bit-exact (counter-based RNG).  CBOW: vectors within the fp32-reassociation tolerance."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_gpus_equal_one_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = min(torch.cuda.device_count(), 4)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "mgpu.npz")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), out]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    z = np.load(out)
+    rp, col, w = helpers.ex_graph(1)
+    want, wl = oracle.walks(rp, col, oracle.quantise_weights(w), 80, 7, 1, 0, 2 * 7523)
+    assert (z["nodes"] == want).all() and (z["lens"] == wl).all()
+    (rowptr, gene, label), _ = helpers.ex_windows(reps=2)
+    N = len(rowptr) - 1
+    tr, va = oracle.split_indices(N, 0)
+    W0, Wo0 = helpers.init_weights(7523, 128, 0)
+    ref, hist, _, _ = oracle.cbow_train(rowptr, gene, label, tr, va, W0, Wo0, 0.005, max_steps=5, early_stop=False)
+    assert np.abs(z["W"] - ref).max() < 1e-4 * np.abs(ref).max()
+    for (s_, av, at), row in zip(hist, z["hist"]):
+        assert abs(av - row[1]) <= 2.0 / len(va) + 1e-7 and abs(at - row[2]) <= 2.0 / len(tr) + 1e-7
