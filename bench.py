@@ -47,6 +47,9 @@ def parse():
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     p.add_argument("--reps", type=int, default=10, help="numRepetition per GPU (weak) or in total (strong)")
     p.add_argument("--optimizer", default="adam", choices=["adam", "sgd"])
+    p.add_argument("--algo", default="rows", choices=["rows", "rank1"],
+                   help="CBOW formulation the headline value is measured on (rows = north_star's gather/scatter kernel)")
+    p.add_argument("--no-alt-algo", action="store_true", help="do not also time the other formulation")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--cpu-sample-windows", type=int, default=32768)
@@ -63,6 +66,16 @@ def workload(name):
     V, E, D, L = graph.BENCH_CONFIGS[name]
     gs = [graph.synthetic_graph(V, E, g) for g in (0, 1)]
     return gs, V, D, L, "synthetic directed ER, %d genes / %d edges per group, weights U(0.5,1)" % (V, E)
+
+
+def traffic_lookup(kernel, workload_name):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the named kernel on the named
+    workload from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[kernel][workload_name]["dram_bytes"]
+    except Exception:
+        return None
 
 
 def peaks():
@@ -228,44 +241,79 @@ def run_b200(args):
     tr, va = cbow.split_indices(N_loc, 1000 + rank)
     n_tr_tot, n_va_tot = int(allsum(len(tr))), int(allsum(len(va)))
     W0, Wo0 = cbow.init_weights(V, D, 0)
-    model = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, optimizer=args.optimizer, lr=0.005)
     tr_d = torch.from_numpy(tr.astype(np.int32)).to(dev); va_d = torch.from_numpy(va.astype(np.int32)).to(dev)
     acc_pin = torch.zeros(4, dtype=torch.int64).pin_memory()
-
-    def cbow_step(m_fb=None, m_upd=None):
-        model.acc.zero_()
-        model.fwdbwd(tr_d, n_tr_tot)
-        if m_fb is not None:
-            m_fb.record()
-        if world > 1:
-            dist.all_reduce(model.g_ih); dist.all_reduce(model.g_ho)
-        model.update()
-        if m_upd is not None:
-            m_upd.record()
-        model.evaluate(va_d, 2)
-        model.evaluate(tr_d, 3)
-        if world > 1:
-            dist.all_reduce(model.acc[2:4])
-        acc_pin.copy_(model.acc, non_blocking=True)
-
-    timed(cbow_step, W)
-    barrier()
-    l0 = _capi.launch_count()
-    ct, marks = timed(cbow_step, K, marks=2)
-    barrier()
-    cbow_launches = _capi.launch_count() - l0
-    step_ms = allmax(float(np.mean(ct)))
-    fb_ms = float(np.mean([m[0] for m in marks]))
-    upd_ms = allmax(float(np.mean([m[1] for m in marks])))
-    acc_val = int(acc_pin[2]) / max(n_va_tot, 1)
-    value = n_tr_tot / (step_ms * 1e-3)
-
-    # algorithmic bytes of the fused fwd+bwd kernel on this rank: per window l*(8D+4)+5  
     ltr = lens_np[tr]
-    fb_bytes = int((ltr * (8 * D + 4) + 5).sum())
-    opt_bytes = (32 if args.optimizer == "adam" else 16) * V * D
     peak, peak_src = peaks()
-    fb_gbs = fb_bytes / (fb_ms * 1e-3) / 1e9
+    l2_bytes = 126e6
+
+    def make_step(model):
+        def cbow_step(m_fb=None, m_upd=None):
+            model.acc.zero_()
+            model.fwdbwd(tr_d, n_tr_tot)
+            if m_fb is not None:
+                m_fb.record()
+            if world > 1:
+                for g in model.grad_tensors():
+                    dist.all_reduce(g)
+            model.update()
+            if m_upd is not None:
+                m_upd.record()
+            model.evaluate(va_d, 2)
+            model.evaluate(tr_d, 3)
+            if world > 1:
+                dist.all_reduce(model.acc[2:4])
+            acc_pin.copy_(model.acc, non_blocking=True)
+        return cbow_step
+
+    def measure(algo):
+        model = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, optimizer=args.optimizer, lr=0.005, algo=algo)
+        step = make_step(model)
+        timed(step, W)
+        barrier()
+        l0 = _capi.launch_count()
+        ct, marks = timed(step, K, marks=2)
+        barrier()
+        r = {"launches": _capi.launch_count() - l0, "step_ms": allmax(float(np.mean(ct))),
+             "fb_ms": float(np.mean([m[0] for m in marks])),
+             "upd_ms": allmax(float(np.mean([m[1] for m in marks]))),
+             "acc_val": int(acc_pin[2]) / max(n_va_tot, 1), "model": model, "step": step}
+        r["value"] = n_tr_tot / (r["step_ms"] * 1e-3)
+        return r
+
+    def roofline_of(algo, r):
+        opt_b = (32 if args.optimizer == "adam" else 16) * V * D
+        if algo == "rows":
+            b = int((ltr * (8 * D + 4) + 5).sum())          # l*(8D+4)+5 per window
+            gbs = b / (r["fb_ms"] * 1e-3) / 1e9
+            resident = V * D * 4 < l2_bytes
+            return {"kernel": "cbow_rows_kernel<%d,true> (fused gather/sum/logit/BCE/scatter-add)" % max(D // 128, 0),
+                    "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                    "traffic": traffic_lookup("cbow_rows_fwdbwd", args.workload), "peak_source": peak_src,
+                    "kernel_ms": r["fb_ms"], "algorithmic_bytes_per_launch": b,
+                    "bytes_model": "sum over this rank's training windows of l*(8D+4)+5; the optimizer epilogue "
+                                   "(%d B) is a separate kernel" % opt_b,
+                    "note": ("W_ih + gradient (%.0f MB) are L2-resident at this config: the algorithmic rate can exceed "
+                             "DRAM traffic and the HBM peak" % (2 * V * D * 4 / 1e6)) if resident else
+                            ("W_ih + gradient (%.0f MB) exceed L2: the gather and the scatter-add go to HBM"
+                             % (2 * V * D * 4 / 1e6))}
+        b = (28 if args.optimizer == "adam" else 12) * V * D      # update rows R/W W,m,v + prepare re-read of W
+        ms = r["upd_ms"] - r["fb_ms"]
+        gbs = b / (ms * 1e-3) / 1e9
+        return {"kernel": "r1_update_kernel + r1_update_ho_kernel + r1_prepare_kernel (dense optimizer pass)",
+                "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                "traffic": traffic_lookup("r1_update", args.workload), "peak_source": peak_src, "kernel_ms": ms,
+                "algorithmic_bytes_per_launch": b,
+                "bytes_model": "28*V*D (Adam: read W,m,v + write W,m,v, then re-read W for s); the window kernel moves "
+                               "only %d B (12*l+5 per window) in %.3f ms" % (int((ltr * 12 + 5).sum()), r["fb_ms"])}
+
+    res = {args.algo: measure(args.algo)}
+    alt = "rank1" if args.algo == "rows" else "rows"
+    if not args.no_alt_algo:
+        res[alt] = measure(alt)
+    main = res[args.algo]
+    model, cbow_step = main["model"], main["step"]
+    step_ms, upd_ms, value, acc_val, cbow_launches = main["step_ms"], main["upd_ms"], main["value"], main["acc_val"], main["launches"]
 
     e2e = None
     if not args.no_e2e:
@@ -314,14 +362,14 @@ def run_b200(args):
             "gpu_launches": int(cbow_launches + walk_launches),
             "gpu_launches_total_process": int(total_launches),
             "clocks": clocks,
-            "roofline": {"kernel": "cbow_rows_kernel<%d,true> (fused gather/sum/logit/BCE/scatter-add)" % (D // 128),
-                         "bound": "hbm", "achieved": fb_gbs, "peak": peak, "unit": "GB/s", "frac": fb_gbs / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": fb_ms,
-                         "algorithmic_bytes_per_launch": fb_bytes,
-                         "bytes_model": "sum over training windows of l*(8D+4)+5; optimizer epilogue (%d B) is a "
-                                        "separate kernel" % opt_bytes,
-                         "note": "W_ih (%.1f MB) is L2-resident at this config: the algorithmic rate can exceed "
-                                 "DRAM traffic" % (V * D * 4 / 1e6)},
+            "roofline": roofline_of(args.algo, main),
+            "algo": args.algo,
+            "alt_algo": None if alt not in res else {
+                "algo": alt, "value": res[alt]["value"], "unit": UNIT, "ms_per_step": res[alt]["step_ms"],
+                "train_only_ms": res[alt]["upd_ms"], "acc_val_last": res[alt]["acc_val"],
+                "roofline": roofline_of(alt, res[alt]),
+                "note": "rank1 = collapsed trainer (s = W_ih.W_ho, c = X^T.dO; SURVEY 8f-3), same results up to fp32 "
+                        "reassociation; rows = north_star's embedding-row gather/scatter kernel"},
             "cpu_baseline": cpu,
             "walk": {"metric": "random_walk_steps_per_sec", "value": visits / (walk_ms * 1e-3), "unit": "steps/s",
                      "ms_per_pass": walk_ms, "walkers": int(allsum(2 * n_walk)) if world > 1 else 2 * n_walk,

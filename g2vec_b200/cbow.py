@@ -58,7 +58,7 @@ class CbowModel:
     """Parameters + optimizer state + scratch in HBM, and the three kernel calls."""
 
     def __init__(self, rowptr, gene, label, n_genes, hidden, W_ih0, W_ho0, optimizer="adam", reduce="sum",
-                 lr=0.005, beta1=0.9, beta2=0.999, eps=1e-8, device=None):
+                 lr=0.005, beta1=0.9, beta2=0.999, eps=1e-8, device=None, algo="rows"):
         if not torch.cuda.is_available():
             raise RuntimeError("g2vec_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _capi.load()
@@ -80,7 +80,16 @@ class CbowModel:
         self.reduce = {"sum": _capi.REDUCE_SUM, "mean": _capi.REDUCE_MEAN}[reduce]
         self.lr, self.beta1, self.beta2, self.eps = float(lr), float(beta1), float(beta2), float(eps)
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-        self.g_ih, self.g_ho = z(self.V, self.D), z(self.D)
+        if algo not in ("rows", "rank1"):
+            raise ValueError("algo must be 'rows' (gather/scatter of embedding rows) or 'rank1' (collapsed)")
+        self.algo = algo
+        self.g_ho = z(self.D)
+        if algo == "rows":
+            self.g_ih = z(self.V, self.D)
+            self.s = self.c = None
+        else:                       # rank-1: s = W_ih.W_ho, c = X^T.dO; no dense gradient
+            self.g_ih = None
+            self.s, self.c = z(self.V), z(self.V)
         if self.opt == _capi.OPT_ADAM_TF1:
             self.m_ih, self.v_ih, self.m_ho, self.v_ho = z(self.V, self.D), z(self.V, self.D), z(self.D), z(self.D)
         else:
@@ -88,6 +97,13 @@ class CbowModel:
         # [loss_sum (f64 bits), n_correct_train_fwd, n_correct_val, n_correct_train] as 4 x 8 bytes
         self.acc = torch.zeros(4, dtype=torch.int64, device=dev)
         self.t = 0
+        if algo == "rank1":
+            _capi.check(self.lib.g2v_cbow_r1_prepare(self.W_ih.data_ptr(), self.W_ho.data_ptr(), self.s.data_ptr(),
+                                                     self.V, self.D, self._stream()), "g2v_cbow_r1_prepare")
+
+    def grad_tensors(self):
+        """What a multi-GPU step must all-reduce (sum) between fwdbwd() and update()."""
+        return [self.g_ih, self.g_ho] if self.algo == "rows" else [self.c]
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -100,6 +116,13 @@ class CbowModel:
         """Accumulate the gradient of the listed windows into g_ih / g_ho (loss sum -> acc[0],
         pre-update correct count -> acc[1])."""
         n = (win.shape[0] - win_begin) if n_win is None else n_win
+        if self.algo == "rank1":
+            rc = self.lib.g2v_cbow_r1_windows(self.rowptr.data_ptr(), self.gene.data_ptr(), self.label.data_ptr(),
+                                              self._ptr(win), int(win_begin), int(n), 1.0 / float(n_total),
+                                              self.s.data_ptr(), self.c.data_ptr(), self.acc.data_ptr(),
+                                              self.acc.data_ptr() + 8, self.V, self.reduce, self._stream())
+            _capi.check(rc, "g2v_cbow_r1_windows")
+            return
         rc = self.lib.g2v_cbow_fwdbwd(self.rowptr.data_ptr(), self.gene.data_ptr(), self.label.data_ptr(),
                                       self._ptr(win), int(win_begin), int(n), 1.0 / float(n_total),
                                       self.W_ih.data_ptr(), self.W_ho.data_ptr(), self.g_ih.data_ptr(),
@@ -109,6 +132,14 @@ class CbowModel:
 
     def update(self):
         self.t += 1
+        if self.algo == "rank1":
+            rc = self.lib.g2v_cbow_r1_update(self.W_ih.data_ptr(), self.W_ho.data_ptr(), self._ptr(self.m_ih),
+                                             self._ptr(self.v_ih), self._ptr(self.m_ho), self._ptr(self.v_ho),
+                                             self.c.data_ptr(), self.g_ho.data_ptr(), self.s.data_ptr(), self.V,
+                                             self.D, self.opt, self.lr, self.beta1, self.beta2, self.eps, self.t,
+                                             self._stream())
+            _capi.check(rc, "g2v_cbow_r1_update")
+            return
         rc = self.lib.g2v_cbow_update(self.W_ih.data_ptr(), self.W_ho.data_ptr(), self._ptr(self.m_ih),
                                       self._ptr(self.v_ih), self._ptr(self.m_ho), self._ptr(self.v_ho),
                                       self.g_ih.data_ptr(), self.g_ho.data_ptr(), self.V, self.D, self.opt,
@@ -118,6 +149,12 @@ class CbowModel:
     def evaluate(self, win, slot, win_begin=0, n_win=None):
         """Add the number of correctly classified listed windows into acc[slot]."""
         n = (win.shape[0] - win_begin) if n_win is None else n_win
+        if self.algo == "rank1":
+            rc = self.lib.g2v_cbow_r1_windows(self.rowptr.data_ptr(), self.gene.data_ptr(), self.label.data_ptr(),
+                                              self._ptr(win), int(win_begin), int(n), 0.0, self.s.data_ptr(), 0, 0,
+                                              self.acc.data_ptr() + 8 * slot, self.V, self.reduce, self._stream())
+            _capi.check(rc, "g2v_cbow_r1_windows")
+            return
         rc = self.lib.g2v_cbow_eval(self.rowptr.data_ptr(), self.gene.data_ptr(), self.label.data_ptr(),
                                     self._ptr(win), int(win_begin), int(n), self.W_ih.data_ptr(),
                                     self.W_ho.data_ptr(), self.acc.data_ptr() + 8 * slot, self.V, self.D,
@@ -137,7 +174,7 @@ def _dist():
 
 def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500, seed=0, optimizer="adam",
                reduce="sum", W_ih0=None, W_ho0=None, split=None, early_stop=True, log=print, return_info=False,
-               eval_train="lazy"):
+               eval_train="lazy", algo="rows"):
     """Train the modified CBOW on CSR windows and return W_ih (np.float32 [n_genes, hidden]) exactly as
     ``compute_genetovec`` does: the weights after the last step whose validation accuracy did not drop.
 
@@ -153,7 +190,7 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
     tr, va = split_indices(N, seed) if split is None else split
     if W_ih0 is None or W_ho0 is None:
         W_ih0, W_ho0 = init_weights(n_genes, hidden, seed)
-    model = CbowModel(win_rowptr, win_gene, labels, n_genes, hidden, W_ih0, W_ho0, optimizer, reduce, lr)
+    model = CbowModel(win_rowptr, win_gene, labels, n_genes, hidden, W_ih0, W_ho0, optimizer, reduce, lr, algo=algo)
     lens = np.diff(rowptr_np).astype(np.int64)
     n_tr, n_va = len(tr), len(va)
     tr_loc, va_loc = shard_by_nnz(np.asarray(tr), lens, world, rank), shard_by_nnz(np.asarray(va), lens, world, rank)
@@ -173,8 +210,8 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
         if len(tr_loc):
             model.fwdbwd(tr_d, n_tr)          # acc[1] += correct predictions with the PRE-update weights
         if dist:
-            dist.all_reduce(model.g_ih)
-            dist.all_reduce(model.g_ho)
+            for g in model.grad_tensors():
+                dist.all_reduce(g)
         model.update()
         if len(va_loc):
             model.evaluate(va_d, 2)

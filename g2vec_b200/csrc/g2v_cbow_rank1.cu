@@ -1,0 +1,312 @@
+// g2v_cbow_rank1.cu -- HOT PATH 2, collapsed form.
+//
+// The reference's model has no nonlinearity:  O = (X.W_ih).W_ho = X.(W_ih.W_ho)  (G2Vec.py:239-240).
+// With  s = W_ih.W_ho  [V]  and  c = X^T.dO  [V]  the same optimizer step is, exactly,
+//     o[n]     = sum_{g in window n} s[g]
+//     dO[n]    = (sigmoid(o[n]) - y[n]) / N
+//     dW_ih[g] = c[g] * W_ho            (rank-1: the dense [V,D] gradient is never formed)
+//     dW_ho    = W_ih^T . c
+// so the per-window work touches 4-byte scalars instead of D-wide rows, and the only dense traffic
+// is the optimizer pass itself.  Results differ from the row formulation by float32 reassociation only
+// (tests/test_gpu_cbow.py holds both to the same oracle and tolerance).
+//
+//   r1_prepare_kernel   s[g] = <W_ih[g,:], W_ho>                        reads 4*V*D
+//   r1_windows_kernel   per window: gather s, logit, loss/acc, dO, c[g] += dO   12*l + 5 bytes / window
+//   r1_update_kernel    per row: g = c[g]*W_ho, g_ho += c[g]*W_ih[g,:], Adam/SGD on the row   24*V*D (Adam)
+//   r1_update_ho_kernel Adam/SGD on W_ho from g_ho
+// Multi-GPU exchanges only c (4*V bytes) per step instead of the dense gradient (4*V*D bytes).
+#include "g2v_common.cuh"
+
+namespace g2v {
+
+constexpr int kR1Warps = 8;
+
+__device__ __forceinline__ float sigmoid_stable_r1(float x) {
+    if (x >= 0.f) { const float z = expf(-x); return 1.f / (1.f + z); }
+    const float z = expf(x);
+    return z / (1.f + z);
+}
+
+__device__ __forceinline__ void adam1_r1(float &w, float &m, float &v, float g, float alpha, float omb1,
+                                         float omb2, float eps) {
+    m += (g - m) * omb1;
+    v += (g * g - v) * omb2;
+    w -= (m * alpha) / (sqrtf(v) + eps);
+}
+
+// ---- s = W_ih . W_ho ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kR1Warps * 32)
+r1_prepare_kernel(const float *__restrict__ W_ih, const float *__restrict__ W_ho, float *__restrict__ s,
+                  int32_t V, int32_t D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kR1Warps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kR1Warps;
+    const bool vec4 = (D & 3) == 0;
+    for (int64_t g = warp; g < V; g += nwarps) {
+        const float *row = W_ih + (size_t)g * D;
+        float part = 0.f;
+        if (vec4) {
+            const float4 *r4 = reinterpret_cast<const float4 *>(row);
+            const float4 *h4 = reinterpret_cast<const float4 *>(W_ho);
+            for (int i = lane; i < (D >> 2); i += 32) {
+                const float4 a = __ldg(r4 + i), b = __ldg(h4 + i);
+                part += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+            }
+        } else {
+            for (int d = lane; d < D; d += 32) part += __ldg(row + d) * __ldg(W_ho + d);
+        }
+        part = warp_sum(part);
+        if (lane == 0) s[g] = part;
+    }
+}
+
+// ---- per-window forward (+ backward into c) -------------------------------------------------------
+struct R1Acc { double loss; unsigned long long correct; };
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(kR1Warps * 32)
+r1_windows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ gene,
+                  const uint8_t *__restrict__ label, const int32_t *__restrict__ win, int64_t win_begin,
+                  int64_t n_win, float inv_n, const float *__restrict__ s, float *__restrict__ c,
+                  double *__restrict__ loss_sum, unsigned long long *__restrict__ n_correct,
+                  int32_t reduce_mean) {
+    __shared__ R1Acc sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { sh.loss = 0.0; sh.correct = 0ull; }
+    __syncthreads();
+    float loss_acc = 0.f;
+    unsigned correct_acc = 0;
+    const int64_t warps_total = (int64_t)gridDim.x * kR1Warps;
+    for (int64_t i = (int64_t)blockIdx.x * kR1Warps + warp; i < n_win; i += warps_total) {
+        const int64_t n = win ? (int64_t)__ldg(win + win_begin + i) : win_begin + i;
+        const int32_t b = __ldg(rowptr + n), e = __ldg(rowptr + n + 1);
+        const float y = (float)__ldg(label + n);
+        float part = 0.f;
+        for (int32_t j = b + lane; j < e; j += 32) part += __ldg(s + __ldg(gene + j));
+        const float scale = (reduce_mean && e > b) ? 1.f / (float)(e - b) : 1.f;
+        const float o = warp_sum(part) * scale;
+        if (lane == 0) {
+            correct_acc += ((o > 0.f) == (y != 0.f)) ? 1u : 0u;
+            if (BACKWARD) loss_acc += fmaxf(o, 0.f) - o * y + log1pf(expf(-fabsf(o)));
+        }
+        if (BACKWARD) {
+            const float dO = (sigmoid_stable_r1(o) - y) * inv_n * scale;
+            for (int32_t j = b + lane; j < e; j += 32) atomicAdd(c + __ldg(gene + j), dO);
+        }
+    }
+    if (lane == 0) {
+        if (BACKWARD) atomicAdd(&sh.loss, (double)loss_acc);
+        atomicAdd(&sh.correct, (unsigned long long)correct_acc);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (BACKWARD && loss_sum) atomicAdd(loss_sum, sh.loss);
+        if (n_correct) atomicAdd(n_correct, sh.correct);
+    }
+}
+
+// ---- dense optimizer pass over the rows -----------------------------------------------------------
+// VEC > 0: D = 128*VEC, register accumulators for g_ho.  VEC == 0: any D, shared-memory accumulators.
+template <int VEC, int OPT>
+__global__ void __launch_bounds__(kR1Warps * 32)
+r1_update_kernel(float *__restrict__ W_ih, float *__restrict__ M, float *__restrict__ Vv,
+                 const float *__restrict__ W_ho, float *__restrict__ c, float *__restrict__ g_ho, int32_t V,
+                 int32_t D, float alpha, float omb1, float omb2, float eps) {
+    extern __shared__ float sh_gho[];              // [D]
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) sh_gho[i] = 0.f;
+    __syncthreads();
+    const int64_t warp = (int64_t)blockIdx.x * kR1Warps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kR1Warps;
+    if (VEC > 0) {
+        constexpr int NV = VEC > 0 ? VEC : 1;  // (dead code when VEC == 0)
+        float4 who[NV], acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            who[v] = __ldg(reinterpret_cast<const float4 *>(W_ho) + v * 32 + lane);
+            acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int64_t g = warp; g < V; g += nwarps) {
+            const float cg = c[g];
+            float4 *w4 = reinterpret_cast<float4 *>(W_ih + (size_t)g * D) + lane;
+            float4 *m4 = reinterpret_cast<float4 *>(M + (size_t)g * D) + lane;
+            float4 *v4 = reinterpret_cast<float4 *>(Vv + (size_t)g * D) + lane;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                float4 w = w4[v * 32];
+                acc[v].x += cg * w.x; acc[v].y += cg * w.y; acc[v].z += cg * w.z; acc[v].w += cg * w.w;
+                if (OPT == G2V_OPT_ADAM_TF1) {
+                    float4 m = m4[v * 32], vv = v4[v * 32];
+                    adam1_r1(w.x, m.x, vv.x, cg * who[v].x, alpha, omb1, omb2, eps);
+                    adam1_r1(w.y, m.y, vv.y, cg * who[v].y, alpha, omb1, omb2, eps);
+                    adam1_r1(w.z, m.z, vv.z, cg * who[v].z, alpha, omb1, omb2, eps);
+                    adam1_r1(w.w, m.w, vv.w, cg * who[v].w, alpha, omb1, omb2, eps);
+                    m4[v * 32] = m; v4[v * 32] = vv;
+                    w4[v * 32] = w;
+                } else if (cg != 0.f) {
+                    w.x -= alpha * cg * who[v].x; w.y -= alpha * cg * who[v].y;
+                    w.z -= alpha * cg * who[v].z; w.w -= alpha * cg * who[v].w;
+                    w4[v * 32] = w;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) c[g] = 0.f;
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            float *p = sh_gho + (v * 32 + lane) * 4;
+            atomicAdd(p + 0, acc[v].x); atomicAdd(p + 1, acc[v].y);
+            atomicAdd(p + 2, acc[v].z); atomicAdd(p + 3, acc[v].w);
+        }
+    } else {
+        for (int64_t g = warp; g < V; g += nwarps) {
+            const float cg = c[g];
+            float *w = W_ih + (size_t)g * D;
+            for (int d = lane; d < D; d += 32) {
+                float x = w[d];
+                if (cg != 0.f) atomicAdd(sh_gho + d, cg * x);
+                if (OPT == G2V_OPT_ADAM_TF1) {
+                    float m = M[(size_t)g * D + d], vv = Vv[(size_t)g * D + d];
+                    adam1_r1(x, m, vv, cg * __ldg(W_ho + d), alpha, omb1, omb2, eps);
+                    M[(size_t)g * D + d] = m; Vv[(size_t)g * D + d] = vv;
+                } else {
+                    x -= alpha * cg * __ldg(W_ho + d);
+                }
+                w[d] = x;
+            }
+            __syncwarp();
+            if (lane == 0) c[g] = 0.f;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float x = sh_gho[i];
+        if (x != 0.f) atomicAdd(g_ho + i, x);
+    }
+}
+
+template <int OPT>
+__global__ void r1_update_ho_kernel(float *__restrict__ W_ho, float *__restrict__ m, float *__restrict__ v,
+                                    float *__restrict__ g_ho, int32_t D, float alpha, float omb1, float omb2,
+                                    float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < D) {
+        float w = W_ho[i];
+        const float g = g_ho[i];
+        if (OPT == G2V_OPT_ADAM_TF1) {
+            float mm = m[i], vv = v[i];
+            adam1_r1(w, mm, vv, g, alpha, omb1, omb2, eps);
+            m[i] = mm; v[i] = vv;
+        } else {
+            w -= alpha * g;
+        }
+        W_ho[i] = w;
+        g_ho[i] = 0.f;
+    }
+}
+
+static int r1_grid(const void *kernel, size_t smem, int64_t items, int *grid_out) {
+    DeviceProps dp;
+    if (device_props(&dp)) return 1;
+    if (dp.cc_major != 10) { set_error("needs an sm_100 device (found sm_%d%d); no CPU fallback", dp.cc_major, dp.cc_minor); return 2; }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kR1Warps * 32, smem);
+    if (e != cudaSuccess || per_sm <= 0) { set_error("occupancy query failed: %s", cudaGetErrorString(e)); return 1; }
+    int64_t grid = (int64_t)dp.sm_count * per_sm;
+    const int64_t need = (items + kR1Warps - 1) / kR1Warps;
+    if (grid > need) grid = need;
+    *grid_out = (int)(grid > 0 ? grid : 1);
+    return 0;
+}
+
+}  // namespace g2v
+
+using namespace g2v;
+
+extern "C" int g2v_cbow_r1_prepare(const float *W_ih, const float *W_ho, float *s, int32_t V, int32_t D,
+                                   void *stream) {
+    G2V_REQUIRE(V > 0 && D > 0 && W_ih && W_ho && s, "g2v_cbow_r1_prepare: bad arguments");
+    int grid = 0, rc;
+    if ((rc = r1_grid((const void *)r1_prepare_kernel, 0, V, &grid))) return rc;
+    r1_prepare_kernel<<<grid, kR1Warps * 32, 0, (cudaStream_t)stream>>>(W_ih, W_ho, s, V, D);
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int g2v_cbow_r1_windows(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
+                                   const int32_t *win, int64_t win_begin, int64_t n_win, float inv_n_total,
+                                   const float *s, float *c, double *loss_sum, int64_t *n_correct, int32_t V,
+                                   int32_t reduce, void *stream) {
+    G2V_REQUIRE(V > 0 && n_win >= 0 && win_begin >= 0, "g2v_cbow_r1_windows: bad sizes");
+    G2V_REQUIRE(rowptr && label && s, "g2v_cbow_r1_windows: null pointer");
+    G2V_REQUIRE(reduce == G2V_REDUCE_SUM || reduce == G2V_REDUCE_MEAN, "g2v_cbow_r1_windows: unknown reduce %d", reduce);
+    if (n_win == 0) return 0;
+    unsigned long long *nc = reinterpret_cast<unsigned long long *>(n_correct);
+    int grid = 0, rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c) {
+        if ((rc = r1_grid((const void *)r1_windows_kernel<true>, 0, n_win, &grid))) return rc;
+        r1_windows_kernel<true><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, win_begin, n_win,
+                                                               inv_n_total, s, c, loss_sum, nc, reduce);
+    } else {
+        if ((rc = r1_grid((const void *)r1_windows_kernel<false>, 0, n_win, &grid))) return rc;
+        r1_windows_kernel<false><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, win_begin, n_win, 0.f,
+                                                                s, nullptr, nullptr, nc, reduce);
+    }
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+template <int VEC, int OPT>
+static int launch_r1_update(float *W_ih, float *M, float *Vv, const float *W_ho, float *c, float *g_ho, int32_t V,
+                            int32_t D, float alpha, float omb1, float omb2, float eps, cudaStream_t st) {
+    const size_t smem = (size_t)D * sizeof(float);
+    DeviceProps dp;
+    if (device_props(&dp)) return 1;
+    G2V_REQUIRE(smem <= (size_t)dp.max_smem_optin, "sizeHiddenlayer %d too large", D);
+    if (smem > 48 * 1024)
+        G2V_CUDA_OK(cudaFuncSetAttribute(r1_update_kernel<VEC, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = 0, rc;
+    if ((rc = r1_grid((const void *)r1_update_kernel<VEC, OPT>, smem, V, &grid))) return rc;
+    r1_update_kernel<VEC, OPT><<<grid, kR1Warps * 32, smem, st>>>(W_ih, M, Vv, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps);
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
+                                  float *c, float *g_ho, float *s, int32_t V, int32_t D, int32_t optimizer,
+                                  float lr, float beta1, float beta2, float eps, int32_t t, void *stream) {
+    G2V_REQUIRE(V > 0 && D > 0 && t >= 1, "g2v_cbow_r1_update: bad sizes (V=%d D=%d t=%d)", V, D, t);
+    G2V_REQUIRE(W_ih && W_ho && c && g_ho && s, "g2v_cbow_r1_update: null pointer");
+    G2V_REQUIRE(optimizer == G2V_OPT_ADAM_TF1 || optimizer == G2V_OPT_SGD, "g2v_cbow_r1_update: unknown optimizer %d", optimizer);
+    G2V_REQUIRE(optimizer == G2V_OPT_SGD || (m_ih && v_ih && m_ho && v_ho), "g2v_cbow_r1_update: Adam needs m/v buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    float alpha = lr, omb1 = 0.f, omb2 = 0.f;
+    if (optimizer == G2V_OPT_ADAM_TF1) {
+        float b1p = 1.f, b2p = 1.f;
+        for (int i = 0; i < t; ++i) { b1p *= beta1; b2p *= beta2; }
+        alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+        omb1 = 1.f - beta1; omb2 = 1.f - beta2;
+    }
+    int rc;
+#define G2V_R1(VEC)                                                                                             \
+    rc = optimizer == G2V_OPT_ADAM_TF1                                                                          \
+             ? launch_r1_update<VEC, G2V_OPT_ADAM_TF1>(W_ih, m_ih, v_ih, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps, st) \
+             : launch_r1_update<VEC, G2V_OPT_SGD>(W_ih, nullptr, nullptr, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps, st)
+    if (D == 128) { G2V_R1(1); }
+    else if (D == 256) { G2V_R1(2); }
+    else if (D == 512) { G2V_R1(4); }
+    else { G2V_R1(0); }
+#undef G2V_R1
+    if (rc) return rc;
+    if (optimizer == G2V_OPT_ADAM_TF1)
+        r1_update_ho_kernel<G2V_OPT_ADAM_TF1><<<(D + 127) / 128, 128, 0, st>>>(W_ho, m_ho, v_ho, g_ho, D, alpha, omb1, omb2, eps);
+    else
+        r1_update_ho_kernel<G2V_OPT_SGD><<<(D + 127) / 128, 128, 0, st>>>(W_ho, nullptr, nullptr, g_ho, D, alpha, omb1, omb2, eps);
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return g2v_cbow_r1_prepare(W_ih, W_ho, s, V, D, stream);
+}

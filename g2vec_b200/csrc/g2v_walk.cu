@@ -10,8 +10,9 @@
 // Layout: the group's graph as CSR in HBM (rowptr int32 [V+1], col int32 [E] ascending per
 // row, qw uint32 [E]); both are read with coalesced 128 B warp loads (32 neighbours per
 // request).  Per warp in shared memory: the path (L ints, written back once, coalesced) and
-// an open-addressing hash set of the visited nodes (>= 3L slots, so membership is ~1 probe
-// and independent of V).  Neighbour chunks are kept in registers between the two passes
+// the visited set -- a V-bit bitmap (one LDS per neighbour) while 8 warps' bitmaps fit in 56 KB
+// (V <= ~46k at L = 80), otherwise an open-addressing hash set of >= 3L slots whose size is
+// independent of V (200k-node graphs keep full occupancy).  Neighbour chunks are kept in registers between the two passes
 // (total, then selection); rows longer than 32*KC neighbours re-read the tail (L1/L2 hits).
 // Walkers are handed out by an atomic ticket so that warps whose walker dead-ends early
 // (62 % of ex_* start nodes have no out-edge) immediately take the next one.
@@ -19,6 +20,8 @@
 // Integer arithmetic only on the selection path => bit-exact against oracle/g2v_oracle.c for
 // any scan order:  T = sum of unvisited qw (uint64), r = mulhi64(x, T), first inclusive
 // prefix > r.
+#include <stdlib.h>
+
 #include "g2v_common.cuh"
 
 namespace g2v {
@@ -30,9 +33,12 @@ __device__ __forceinline__ uint32_t hash_slot(int32_t c, int shift) {
     return ((uint32_t)c * 2654435761u) >> shift;
 }
 
-// true if node c is in the warp's visited set
+// true if node c is in the warp's visited set.  BITMAP: hs is a V-bit bitmap (1 LDS);
+// otherwise an open-addressing hash set of node ids (-1 = empty).
+template <bool BITMAP>
 __device__ __forceinline__ bool visited(const int32_t *__restrict__ hs, uint32_t mask, int shift,
                                         int32_t c) {
+    if (BITMAP) return (hs[c >> 5] >> (c & 31)) & 1;
     uint32_t i = hash_slot(c, shift);
     while (true) {
         int32_t x = hs[i];
@@ -42,6 +48,7 @@ __device__ __forceinline__ bool visited(const int32_t *__restrict__ hs, uint32_t
     }
 }
 
+template <bool BITMAP>
 __global__ void __launch_bounds__(kWalkWarps * 32)
 walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             const uint32_t *__restrict__ qw, int32_t V, int32_t L, int32_t Lpad, int32_t H,
@@ -54,7 +61,7 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
     int32_t *hs = path + Lpad;
     const uint32_t hmask = (uint32_t)H - 1u;
 
-    for (int i = lane; i < H; i += 32) hs[i] = -1;
+    for (int i = lane; i < H; i += 32) hs[i] = BITMAP ? 0 : -1;
     __syncwarp();
 
     while (true) {
@@ -67,76 +74,98 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
         int32_t cur = (int32_t)(w % V);
         int32_t n = 0;
         bool dirty = false;
+        uint32_t dlo = 0, dhi = 0;                       // lane k holds the draw of step (s & ~31) + k
+        int32_t dbase = -1;
 
         for (int32_t s = 0; s < L; ++s) {
-            if (lane == 0) path[n] = cur;
+            path[n] = cur;                               // every lane stores the same value: no divergence
             ++n;
             if (s == L - 1) break;                       // last draw is never appended
             const int32_t b = __ldg(rowptr + cur), e = __ldg(rowptr + cur + 1);
             if (b == e) break;                           // no out-edges: dead end
-            if (lane == 0) {                             // visited.insert(cur)
+            if (BITMAP) {                                // visited.insert(cur), uniform across the warp
+                const int32_t wv = hs[cur >> 5];
+                __syncwarp();
+                hs[cur >> 5] = wv | (1 << (cur & 31));
+            } else {
                 uint32_t i = hash_slot(cur, hshift);
                 while (hs[i] >= 0) i = (i + 1) & hmask;
+                __syncwarp();
                 hs[i] = cur;
             }
             dirty = true;
             __syncwarp();
 
-            // ---- pass 1: total weight of the unvisited out-neighbours
-            uint32_t mq[kKC];
+            // ---- pass 1: weight of the unvisited out-neighbours, per chunk of 32 (REDUX.SUM)
+            uint32_t mq[kKC], tot[kKC];
             int32_t mc[kKC];
-            unsigned long long mysum = 0;
+            unsigned long long T = 0;
 #pragma unroll
             for (int k = 0; k < kKC; ++k) {
-                const int32_t j = b + k * 32 + lane;
-                mq[k] = 0; mc[k] = -1;
-                if (j < e) {
-                    const int32_t c = __ldg(col + j);
-                    const uint32_t q = __ldg(qw + j);
-                    mc[k] = c;
-                    mq[k] = visited(hs, hmask, hshift, c) ? 0u : q;
-                    mysum += mq[k];
+                mq[k] = 0; mc[k] = -1; tot[k] = 0;
+                if (b + k * 32 < e) {                    // warp-uniform
+                    const int32_t j = b + k * 32 + lane;
+                    if (j < e) {
+                        const int32_t c = __ldg(col + j);
+                        const uint32_t q = __ldg(qw + j);
+                        mc[k] = c;
+                        mq[k] = visited<BITMAP>(hs, hmask, hshift, c) ? 0u : q;
+                    }
+                    tot[k] = __reduce_add_sync(0xffffffffu, mq[k]);   // <= 32 * 2^24
+                    T += tot[k];
                 }
             }
-            for (int32_t j = b + kKC * 32 + lane; j < e; j += 32) {
-                const int32_t c = __ldg(col + j);
-                if (!visited(hs, hmask, hshift, c)) mysum += __ldg(qw + j);
+            for (int32_t jb = b + kKC * 32; jb < e; jb += 32) {       // rows longer than 128 neighbours
+                const int32_t j = jb + lane;
+                uint32_t q = 0;
+                if (j < e) q = visited<BITMAP>(hs, hmask, hshift, __ldg(col + j)) ? 0u : __ldg(qw + j);
+                T += __reduce_add_sync(0xffffffffu, q);
             }
-            const unsigned long long T = warp_sum_u64(mysum);
             if (T == 0) break;                           // every neighbour already visited
 
-            // ---- one 64-bit Philox draw per step, r uniform in [0, T)
-            const uint64_t x = draw64(seed, subseq, (uint32_t)s);
-            unsigned long long rem = __umul64hi(x, T);   // r - (weight already scanned)
+            // ---- one 64-bit Philox draw per step, r uniform in [0, T); 32 steps are drawn at once,
+            //      one per lane (counter-based: lane k evaluates step dbase + k)
+            if ((s & ~31) != dbase) {
+                dbase = s & ~31;
+                const uint64_t d = draw64(seed, subseq, (uint32_t)(dbase + lane));
+                dlo = (uint32_t)d; dhi = (uint32_t)(d >> 32);
+            }
+            const uint64_t x = ((uint64_t)__shfl_sync(0xffffffffu, dhi, s & 31) << 32) |
+                               __shfl_sync(0xffffffffu, dlo, s & 31);
+            unsigned long long rem = __umul64hi(x, T);   // r - (weight of the chunks already skipped)
 
-            // ---- pass 2: first neighbour whose inclusive prefix exceeds r
+            // ---- pass 2: chunk that contains r (uniform scalar search), then one warp scan inside it
             int32_t nxt = -1;
+            bool found = false;
 #pragma unroll
             for (int k = 0; k < kKC; ++k) {
-                if (nxt < 0 && b + k * 32 < e) {
-                    const uint32_t incl = warp_inclusive_scan_u32(mq[k], lane);
-                    const unsigned hit = __ballot_sync(0xffffffffu, (unsigned long long)incl > rem);
-                    if (hit) {
+                if (!found && b + k * 32 < e) {
+                    if (rem < (unsigned long long)tot[k]) {
+                        const uint32_t incl = warp_inclusive_scan_u32(mq[k], lane);
+                        const unsigned hit = __ballot_sync(0xffffffffu, incl > (uint32_t)rem);
                         nxt = __shfl_sync(0xffffffffu, mc[k], __ffs(hit) - 1);
+                        found = true;
                     } else {
-                        rem -= __shfl_sync(0xffffffffu, incl, 31);
+                        rem -= tot[k];
                     }
                 }
             }
-            for (int32_t jb = b + kKC * 32; nxt < 0 && jb < e; jb += 32) {
+            for (int32_t jb = b + kKC * 32; !found && jb < e; jb += 32) {
                 const int32_t j = jb + lane;
                 int32_t c = -1;
                 uint32_t q = 0;
                 if (j < e) {
                     c = __ldg(col + j);
-                    q = visited(hs, hmask, hshift, c) ? 0u : __ldg(qw + j);
+                    q = visited<BITMAP>(hs, hmask, hshift, c) ? 0u : __ldg(qw + j);
                 }
-                const uint32_t incl = warp_inclusive_scan_u32(q, lane);
-                const unsigned hit = __ballot_sync(0xffffffffu, (unsigned long long)incl > rem);
-                if (hit) {
+                const uint32_t ct = __reduce_add_sync(0xffffffffu, q);
+                if (rem < (unsigned long long)ct) {
+                    const uint32_t incl = warp_inclusive_scan_u32(q, lane);
+                    const unsigned hit = __ballot_sync(0xffffffffu, incl > (uint32_t)rem);
                     nxt = __shfl_sync(0xffffffffu, c, __ffs(hit) - 1);
+                    found = true;
                 } else {
-                    rem -= __shfl_sync(0xffffffffu, incl, 31);
+                    rem -= ct;
                 }
             }
             cur = nxt;
@@ -149,7 +178,11 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
         if (lane == 0) out_len[t] = n;
         if (dirty) {
             __syncwarp();
-            for (int i = lane; i < H; i += 32) hs[i] = -1;
+            if (BITMAP) {
+                for (int i = lane; i < n; i += 32) hs[path[i] >> 5] = 0;   // only the words this walk touched
+            } else {
+                for (int i = lane; i < H; i += 32) hs[i] = -1;
+            }
         }
         __syncwarp();
     }
@@ -183,26 +216,36 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
     if (device_props(&dp)) return 1;
     G2V_REQUIRE(dp.cc_major == 10, "g2v_walk_launch: needs an sm_100 device (found sm_%d%d)", dp.cc_major, dp.cc_minor);
 
-    int H = 64, hshift = 26;
-    while (H < 3 * L) { H <<= 1; --hshift; }
+    // visited set per warp: a V-bit bitmap when it is small enough to keep >= 4 CTAs per SM, else a hash set
     const int Lpad = (L + 31) & ~31;
+    const int bm_words = (V + 31) / 32;
+    const char *force = getenv("G2V_WALK_VISITED");             // test hook: "hash" / "bitmap"
+    bool bitmap = (size_t)kWalkWarps * (Lpad + bm_words) * sizeof(int32_t) <= 56 * 1024;
+    if (force && force[0] == 'h') bitmap = false;
+    int H = 64, hshift = 26;
+    if (bitmap) {
+        H = bm_words;
+    } else {
+        while (H < 3 * L) { H <<= 1; --hshift; }
+    }
     const size_t smem = (size_t)kWalkWarps * (Lpad + H) * sizeof(int32_t);
     G2V_REQUIRE(smem <= (size_t)dp.max_smem_optin, "g2v_walk_launch: lenPath %d needs %zu B of shared memory", L, smem);
     cudaStream_t st = (cudaStream_t)stream;
-    static bool attr_done = false;
-    if (!attr_done) {
-        G2V_CUDA_OK(cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
-        G2V_CUDA_OK(cudaFuncSetAttribute(walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_done = true;
+    auto kern = bitmap ? walk_kernel<true> : walk_kernel<false>;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[bitmap]) {
+        G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
+        G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_done[bitmap] = true;
     }
     int per_sm = 0;
-    G2V_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_kernel, kWalkWarps * 32, smem));
+    G2V_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWalkWarps * 32, smem));
     G2V_REQUIRE(per_sm > 0, "g2v_walk_launch: kernel does not fit on an SM");
     int64_t grid = (int64_t)dp.sm_count * per_sm;                 // persistent: whole chip resident
     const int64_t need = (n_walkers + kWalkWarps - 1) / kWalkWarps;
     if (grid > need) grid = need;
     G2V_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(unsigned long long), st));
-    walk_kernel<<<(unsigned)grid, kWalkWarps * 32, smem, st>>>(
+    kern<<<(unsigned)grid, kWalkWarps * 32, smem, st>>>(
         rowptr, col, qw, V, L, Lpad, H, hshift, seed, group, walker_begin, n_walkers, walker_stride,
         out_nodes, out_len, (unsigned long long *)workspace);
     G2V_CUDA_OK(cudaGetLastError());

@@ -119,6 +119,32 @@ int g2v_cbow_step_host(const int32_t *rowptr, const int32_t *gene, const uint8_t
                        float eps, int32_t t, double *loss_sum, int64_t *n_correct);
 
 /* ---------------------------------------------------------------------------------------
+ * HOT PATH 2, collapsed ("rank-1") form -- SURVEY.md 8f-3.  The reference's model is linear
+ * (G2Vec.py:239-240: O = (X.W_ih).W_ho), so with  s = W_ih.W_ho [V]  and  c = X^T.dO [V]
+ * the same step is  o = sum_{g in window} s[g];  dW_ih[g,:] = c[g]*W_ho;  dW_ho = W_ih^T.c.
+ * Same results up to float32 reassociation; 4-byte scalars per (window, gene) instead of
+ * D-wide rows, and a 4*V-byte all-reduce (of c) instead of 4*V*D bytes.
+ *
+ * g2v_cbow_r1_prepare: s[g] = <W_ih[g,:], W_ho>.
+ * g2v_cbow_r1_windows: forward over the listed windows from s; if c != NULL also the backward:
+ *   c[gene] += dO for every gene of the window, loss sum and pre-update correct count
+ *   accumulated as in g2v_cbow_fwdbwd.  c == NULL: accuracy pass only (g2v_cbow_eval).
+ * g2v_cbow_r1_update: optimizer epilogue from c (after its all-reduce when multi-GPU): per row
+ *   g = c[g]*W_ho and g_ho += c[g]*W_ih[g,:] (old W_ih), TF1 Adam / SGD on W_ih, then on W_ho,
+ *   zeroes c and g_ho, and refreshes s for the updated parameters.  g_ho: [D] scratch, zero on
+ *   entry and on exit.
+ * ------------------------------------------------------------------------------------- */
+int g2v_cbow_r1_prepare(const float *W_ih, const float *W_ho, float *s, int32_t V, int32_t D,
+                        void *stream);
+int g2v_cbow_r1_windows(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
+                        const int32_t *win, int64_t win_begin, int64_t n_win, float inv_n_total,
+                        const float *s, float *c, double *loss_sum, int64_t *n_correct, int32_t V,
+                        int32_t reduce, void *stream);
+int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
+                       float *c, float *g_ho, float *s, int32_t V, int32_t D, int32_t optimizer,
+                       float lr, float beta1, float beta2, float eps, int32_t t, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Test hooks (used by tests/ only): 64-bit draws 0..n-1 of one walker subsequence from the
  * kernel's own Philox, and the same words from curand's Philox4_32_10 generator
  * (curand_init(seed, subsequence, 0)), to prove the stream is curand-compatible.

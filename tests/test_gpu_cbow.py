@@ -163,3 +163,63 @@ def test_step_host_entry_point(g2v):
     oracle.adam_(Wr, mm, vv, o_gih, 0.005, 1); oracle.adam_(Wor, mo, vo, o_gho, 0.005, 1)
     assert rel_max(W, Wr) < RTOL_VEC and rel_max(Wo, Wor) < RTOL_VEC
     assert rel_max(state[0], mm) < 1e-4 and abs(nc - o_nc) <= 1 and abs(loss / N - o_loss) < 1e-5
+
+
+# ------------------------------------------------------------------ collapsed (rank-1) trainer, SURVEY 8f-3
+@pytest.mark.parametrize("D,optimizer,reduce", [(128, "adam", "sum"), (256, "adam", "sum"), (512, "adam", "sum"),
+                                                (100, "adam", "sum"), (128, "sgd", "sum"), (64, "sgd", "mean"),
+                                                (128, "adam", "mean")])
+def test_rank1_one_step_equals_oracle(g2v, D, optimizer, reduce):
+    import torch
+    V, N = 500, 3000
+    rowptr, gene, label = helpers.random_windows(N, V, 1, 80, seed=D + 1)
+    W0, Wo0 = helpers.init_weights(V, D, 5)
+    win = np.arange(N, dtype=np.int64)
+    m = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, optimizer=optimizer, reduce=reduce, lr=0.005, algo="rank1")
+    m.fwdbwd(None, N, win_begin=0, n_win=N)
+    torch.cuda.synchronize()
+    acc = m.acc.cpu()
+    c = m.c.cpu().numpy().copy()
+    m.update()
+    torch.cuda.synchronize()
+    if reduce == "sum":
+        o_gih, o_gho, o_loss, o_nc = oracle.cbow_grad(rowptr, gene, label, win, N, W0, Wo0)
+        assert abs(m.loss_sum(acc) / N - o_loss) < 1e-5 * max(1.0, abs(o_loss)) and abs(int(acc[1]) - o_nc) <= 2
+    else:   # mean variant: restate densely in float64
+        lens = np.diff(rowptr).astype(np.float64)
+        H = np.stack([W0[gene[rowptr[n]:rowptr[n + 1]]].astype(np.float64).sum(0) / lens[n] for n in range(N)])
+        dO = (1 / (1 + np.exp(-(H @ Wo0.astype(np.float64)))) - label) / N
+        o_gho = (H * dO[:, None]).sum(0)
+        o_gih = np.zeros((V, D))
+        for n in range(N):
+            o_gih[gene[rowptr[n]:rowptr[n + 1]]] += dO[n] / lens[n] * Wo0
+        o_gih = o_gih.astype(np.float32); o_gho = o_gho.astype(np.float32)
+    # rank-1 structure: the dense gradient is c (x) W_ho
+    assert rel_max(np.outer(c, Wo0), o_gih) < 5e-5
+    W, Wo = W0.copy(), Wo0.copy()
+    if optimizer == "adam":
+        mm, vv, mo, vo = np.zeros_like(W), np.zeros_like(W), np.zeros_like(Wo), np.zeros_like(Wo)
+        oracle.adam_(W, mm, vv, o_gih, 0.005, 1); oracle.adam_(Wo, mo, vo, o_gho, 0.005, 1)
+    else:
+        oracle.sgd_(W, o_gih, 0.005); oracle.sgd_(Wo, o_gho, 0.005)
+    assert rel_max(m.W_ih.cpu().numpy(), W) < RTOL_VEC and rel_max(m.W_ho.cpu().numpy(), Wo) < RTOL_VEC
+    assert float(m.c.abs().max()) == 0.0 and float(m.g_ho.abs().max()) == 0.0
+    s_want = W @ Wo
+    assert np.abs(m.s.cpu().numpy() - s_want).max() < 1e-5 * max(1.0, np.abs(s_want).max())
+
+
+def test_rank1_ex_windows_five_steps_match_oracle(g2v):
+    (rowptr, gene, label), _ = helpers.ex_windows(reps=2)
+    V, D = 7523, 128
+    N = len(rowptr) - 1
+    tr, va = oracle.split_indices(N, 0)
+    W0, Wo0 = helpers.init_weights(V, D, 0)
+    want, hist, stop, _ = oracle.cbow_train(rowptr, gene, label, tr, va, W0, Wo0, 0.005, max_steps=5, early_stop=False)
+    got, info = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=5, seed=0, W_ih0=W0, W_ho0=Wo0,
+                               early_stop=False, log=None, return_info=True, algo="rank1")
+    assert rel_max(got, want) < RTOL_VEC
+    for (s, av, at), (s2, av2, at2) in zip(hist, info["history"]):
+        assert abs(av - av2) <= 2.0 / len(va) + 1e-7 and abs(at - at2) <= 2.0 / len(tr) + 1e-7
+    rows, _ = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=5, seed=0, W_ih0=W0, W_ho0=Wo0,
+                             early_stop=False, log=None, return_info=True, algo="rows")
+    assert rel_max(got, rows) < RTOL_VEC

@@ -134,3 +134,20 @@ def test_synthetic_10k_full_size_properties_and_oracle_sample(g2v):
     # oracle on a sample of walkers
     want, wl = oracle.walks(rp, col, q, L, 12345, 0, 17, V * reps, 50)
     assert (got[17::50] == want).all() and (gl[17::50] == wl).all()
+
+
+def test_hash_visited_set_path(g2v, monkeypatch):
+    """Graphs too large for the per-warp bitmap use the hash set; force it on a small graph too."""
+    rp, col, w = helpers.ex_graph(0)
+    q = oracle.quantise_weights(w)
+    want, wl = oracle.walks(rp, col, q, 80, 21, 0, 0, 2 * (len(rp) - 1))
+    monkeypatch.setenv("G2V_WALK_VISITED", "hash")
+    got, gl = run_gpu(g2v, rp, col, q, 80, 2, 21, 0)
+    assert (got == want).all() and (gl == wl).all()
+    monkeypatch.delenv("G2V_WALK_VISITED")
+    from g2vec_b200 import graph
+    rp, col, w = graph.synthetic_graph(120_000, 600_000, 0)                     # V > bitmap limit
+    q = oracle.quantise_weights(w)
+    want, wl = oracle.walks(rp, col, q, 80, 5, 1, 0, 120_000)
+    got, gl = run_gpu(g2v, rp, col, q, 80, 1, 5, 1)
+    assert (got == want).all() and (gl == wl).all() and wl.max() == 80 and wl.min() == 1
