@@ -176,7 +176,7 @@ def main(argv=None):
     dst = np.fromiter((idx[e[1]] for e in network['edge']), dtype=np.int32, count=len(network['edge']))
     rows = []
     for i, _group in enumerate(['g', 'p']):
-        rp, col, w = graph.group_csr(data['expr'], data['label'], i, src, dst)
+        rp, col, w = graph.group_csr_gpu(data['expr'], data['label'], i, src, dst)
         wg = walks.WalkGraph(rp, col, weights=w)
         nodes, lens = walks.generate_paths(wg, args.lenPath, args.numRepetition, seed=args.seed, group=i)
         rows.append(paths.canonical_rows(nodes, lens))

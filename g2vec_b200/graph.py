@@ -86,6 +86,41 @@ def group_csr(expr, label, group, src, dst, threshold=0.5):
     return csr_from_edges(np.asarray(src)[keep], np.asarray(dst)[keep], w[keep], V)
 
 
+def group_csr_gpu(expr, label, group, src, dst, threshold=0.5, device=None):
+    """construct_adjMat (G2Vec.py:370-391) for one group on the GPU: z-scores and per-edge |PCC| by
+    csrc/g2v_pcc.cu, threshold + (src, dest) sort + last-duplicate-wins on the device with torch as
+    plumbing.  Returns device tensors (rowptr int32 [V+1], col int32 [nnz], w float32 [nnz])."""
+    import torch
+    from . import _capi
+    lib = _capi.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("g2vec_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    x = np.ascontiguousarray(np.asarray(expr, dtype=np.float32)[np.asarray(label) == group])
+    S, V = x.shape
+    xd = torch.from_numpy(x).to(dev)
+    sd = torch.from_numpy(np.ascontiguousarray(src, dtype=np.int32)).to(dev)
+    dd = torch.from_numpy(np.ascontiguousarray(dst, dtype=np.int32)).to(dev)
+    E = int(sd.shape[0])
+    z = torch.empty((V, S), dtype=torch.float32, device=dev)
+    w = torch.empty((E,), dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _capi.check(lib.g2v_pcc_zscore(xd.data_ptr(), S, V, z.data_ptr(), st), "g2v_pcc_zscore")
+    _capi.check(lib.g2v_pcc_edge_weights(z.data_ptr(), S, V, sd.data_ptr(), dd.data_ptr(), E, w.data_ptr(), st),
+                "g2v_pcc_edge_weights")
+    keep = w > threshold
+    key = sd[keep].to(torch.int64) * V + dd[keep].to(torch.int64)
+    wk = w[keep]
+    key, order = torch.sort(key, stable=True)
+    wk = wk[order]
+    last = torch.ones_like(key, dtype=torch.bool)
+    last[:-1] = key[1:] != key[:-1]                    # adjMat[src][dest] = w: the last duplicate wins
+    key, wk = key[last], wk[last]
+    rowptr = torch.zeros(V + 1, dtype=torch.int64, device=dev)
+    rowptr[1:] = torch.cumsum(torch.bincount(key // V, minlength=V), dim=0)
+    return rowptr.to(torch.int32), (key % V).to(torch.int32), wk
+
+
 def synthetic_graph(V, E, group, seed=1000):
     """SURVEY.md 8d generator: E distinct ordered pairs (src != dest) uniform over V^2 from
     numpy Generator(PCG64(seed + group)), weights U(0.5, 1.0) float32, sorted by (src, dest)."""

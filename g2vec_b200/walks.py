@@ -33,7 +33,18 @@ class WalkGraph:
         if qw is None:
             if weights is None:
                 raise ValueError("need weights or qw")
-            qw = _graph.quantise_weights(np.asarray(weights.cpu() if isinstance(weights, torch.Tensor) else weights))
+            if isinstance(weights, torch.Tensor) and weights.is_cuda:
+                # same rule as graph.quantise_weights (rint = round-half-even), kept on the device
+                wd = weights.to(torch.float32).double()
+                if wd.numel() and (not bool(torch.isfinite(wd).all()) or bool((wd < 0).any())):
+                    raise ValueError("edge weights must be finite and non-negative")
+                q = torch.round(wd * _graph.Q_ONE)
+                q = torch.where((wd > 0) & (q < 1), torch.ones_like(q), q)
+                if q.numel() and float(q.max()) > _graph.Q_MAX:
+                    raise ValueError("edge weight too large to quantise")
+                qw = q.to(torch.int32)
+            else:
+                qw = _graph.quantise_weights(np.asarray(weights.cpu() if isinstance(weights, torch.Tensor) else weights))
         self.rowptr = _to_dev(rowptr, torch.int32, device)
         self.col = _to_dev(col, torch.int32, device)
         self.qw = _to_dev(qw, torch.int32, device)

@@ -145,6 +145,18 @@ int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float
                        float lr, float beta1, float beta2, float eps, int32_t t, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Upstream of the walks -- edge weighting.  Replaces construct_adjMat /
+ * compute_PCC, G2Vec.py:354-391, for one patient group.
+ * g2v_pcc_zscore: expr [S*V] sample-major (rows = the group's samples, G2Vec.py:378) ->
+ *   z [V*S] gene-major z-scores (population std; 0 for zero-variance genes, :359,366-367).
+ * g2v_pcc_edge_weights: w[e] = |mean_s z[src[e]][s] * z[dst[e]][s]|  (G2Vec.py:362-365,385).
+ * The > 0.5 threshold (:389) and the CSR assembly are done by the caller.
+ * ------------------------------------------------------------------------------------- */
+int g2v_pcc_zscore(const float *expr, int32_t S, int32_t V, float *z, void *stream);
+int g2v_pcc_edge_weights(const float *z, int32_t S, int32_t V, const int32_t *src, const int32_t *dst,
+                         int64_t E, float *w, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Test hooks (used by tests/ only): 64-bit draws 0..n-1 of one walker subsequence from the
  * kernel's own Philox, and the same words from curand's Philox4_32_10 generator
  * (curand_init(seed, subsequence, 0)), to prove the stream is curand-compatible.

@@ -9,6 +9,8 @@ records outputs of its own functions:
                    graphs (isolated nodes, dead ends, full-length walks, L=1).
   glue_small.npz   integrate_pathSet / count_geneFreq (G2Vec.py:288-322) on the sets above.
   pcc_small.npz    construct_adjMat (G2Vec.py:370-391) on a small expression matrix.
+  ex_expr.npz      ex_* restricted expression matrix [135, 7523] + the 216 540 restricted edges as gene
+                   indices (the inputs of construct_adjMat after the reference's steps 1-2).
   ex_graph.npz     ex_* data through the reference's steps 1-3a: n_samples/n_genes/n_edges
                    (README.md:26-28), per-group CSR of construct_adjMat, and
                    generate_pathSet(adjMat, 80, 1) under np.random.seed(0) for group 0.
@@ -124,6 +126,13 @@ def main():
             out["ps0_flat"] = flat; out["ps0_lens"] = lens
             print("group 0 paths (1 repetition, seed 0):", len(ps))
     np.savez_compressed(os.path.join(OUT, "ex_graph.npz"), **out)
+    # the inputs of construct_adjMat after the reference's steps 1-2 (restricted expression + edge list as
+    # gene indices), so that the GPU box can run BASELINE configs[0] from the same data without /root/reference
+    g2i = {g: i for i, g in enumerate(data["gene"])}
+    np.savez_compressed(os.path.join(OUT, "ex_expr.npz"), expr=data["expr"].astype(np.float32),
+                        src=np.array([g2i[e[0]] for e in network["edge"]], dtype=np.int16),
+                        dst=np.array([g2i[e[1]] for e in network["edge"]], dtype=np.int16),
+                        gene=np.array(data["gene"]))
 
 
 if __name__ == "__main__":
