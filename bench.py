@@ -68,12 +68,17 @@ def workload(name):
     return gs, V, D, L, "synthetic directed ER, %d genes / %d edges per group, weights U(0.5,1)" % (V, E)
 
 
+_RUN = {"reps": None, "world": 1}
+
+
 def traffic_lookup(kernel, workload_name):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the named kernel on the named
-    workload from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the named kernel from the
+    committed ncu --set full capture of this same command (profiles/traffic.json); None when no capture
+    exists for this workload / numRepetition / GPU count."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f)[kernel][workload_name]["dram_bytes"]
+            e = json.load(f)[kernel][workload_name]
+        return e["dram_bytes"] if (e.get("reps") == _RUN["reps"] and _RUN["world"] == 1) else None
     except Exception:
         return None
 
@@ -162,6 +167,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     K, W = args.steps, args.warmup
+    _RUN.update(reps=args.reps, world=world)
     gs, V, D, L, desc = workload(args.workload)
     reps_total = args.reps * (world if args.scaling == "weak" else 1)
     graphs = [g2v.WalkGraph(rp, col, weights=w) for rp, col, w in gs]
@@ -375,7 +381,8 @@ def run_b200(args):
                      "ms_per_pass": walk_ms, "walkers": int(allsum(2 * n_walk)) if world > 1 else 2 * n_walk,
                      "visits_per_pass": visits,
                      "roofline": {"kernel": "walk_kernel", "bound": "hbm", "achieved": walk_gbs, "peak": peak,
-                                  "unit": "GB/s", "frac": walk_gbs / peak, "traffic": None,
+                                  "unit": "GB/s", "frac": walk_gbs / peak,
+                                  "traffic": traffic_lookup("walk", args.workload),
                                   "algorithmic_bytes_per_pass": wbytes,
                                   "bytes_model": "4 B per visit + (8 + 8*deg) B per visit that scans its row"},
                      "e2e": walk_e2e, "cpu_baseline": walk_cpu},

@@ -174,12 +174,17 @@ def _dist():
 
 def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500, seed=0, optimizer="adam",
                reduce="sum", W_ih0=None, W_ho0=None, split=None, early_stop=True, log=print, return_info=False,
-               eval_train="lazy", algo="rows"):
+               eval_train="lazy", algo="rows", batch=0):
     """Train the modified CBOW on CSR windows and return W_ih (np.float32 [n_genes, hidden]) exactly as
     ``compute_genetovec`` does: the weights after the last step whose validation accuracy did not drop.
 
     ``max_epoch`` is the reference's ``--epoch`` (parsed at G2Vec.py:515 but ignored there; the loop is
     hard-coded ``range(500)`` at :262) -- the default 500 reproduces the reference.
+
+    ``batch``: 0 (default) = full batch, one optimizer step per epoch over all training windows as the
+    reference does (:262-264).  ``batch = B > 0`` is the north_star's mini-batch variant: the (already
+    shuffled) training windows are cut into consecutive batches of B, one optimizer step (and, multi-GPU,
+    one gradient all-reduce) per batch, loss mean over the batch; ``batch >= n_train`` equals full batch.
     """
     dist = _dist()
     world, rank = (dist.get_world_size(), dist.get_rank()) if dist else (1, 0)
@@ -207,18 +212,33 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
     f32 = np.float32
     for step in range(max_epoch):
         model.acc.zero_()
-        if len(tr_loc):
-            model.fwdbwd(tr_d, n_tr)          # acc[1] += correct predictions with the PRE-update weights
-        if dist:
-            for g in model.grad_tensors():
-                dist.all_reduce(g)
-        model.update()
+        if batch <= 0 or batch >= n_tr:
+            if len(tr_loc):
+                model.fwdbwd(tr_d, n_tr)      # acc[1] += correct predictions with the PRE-update weights
+            if dist:
+                for g in model.grad_tensors():
+                    dist.all_reduce(g)
+            model.update()
+        else:                                 # mini-batches: every rank takes its 1/world slice of each batch
+            per = -(-batch // world)
+            for lo in range(0, len(tr_loc), per):
+                nb = min(per, len(tr_loc) - lo)
+                nb_tot = nb if not dist else None
+                if dist:
+                    t_nb = torch.tensor([nb], dtype=torch.int64, device=dev); dist.all_reduce(t_nb)
+                    nb_tot = int(t_nb[0])
+                model.fwdbwd(tr_d, nb_tot, win_begin=lo, n_win=nb)
+                if dist:
+                    for g in model.grad_tensors():
+                        dist.all_reduce(g)
+                model.update()
         if len(va_loc):
             model.evaluate(va_d, 2)
         # ACC[tr] of G2Vec.py:267 uses the post-update weights, i.e. exactly what the NEXT step's training
         # forward computes.  It is only printed every 5th step and at the stop, so the extra
         # forward pass is run only when its value is shown now; otherwise it arrives one step later for free.
-        show = (step % 5 == 0 and log is not None) or step == max_epoch - 1 or eval_train == "always"
+        show = ((step % 5 == 0 and log is not None) or step == max_epoch - 1 or eval_train == "always"
+                or 0 < batch < n_tr)          # with mini-batches acc[1] mixes weights: always evaluate
         if show and len(tr_loc):
             model.evaluate(tr_d, 3)
         if dist:

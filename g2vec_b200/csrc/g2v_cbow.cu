@@ -16,11 +16,15 @@
 //
 // No tensor cores: the 128..512-wide reduction is a memory-bound gather/scatter, not a dense
 // contraction.  Algorithmic bytes per window: l*(8D+4)+5, per step + 32*V*D (Adam).
+#include <stdlib.h>
+
 #include "g2v_common.cuh"
 
 namespace g2v {
 
 constexpr int kCbowWarps = 8;
+constexpr bool kDefaultGatherTma = false;
+constexpr bool kDefaultScatterTma = false;   // see profiles/README.md for the measurement behind this choice
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 __device__ __forceinline__ void red_add4(float *p, float4 v) {
@@ -39,7 +43,14 @@ struct CtaAcc {   // per-CTA accumulators in shared memory
     unsigned long long correct;
 };
 
-template <int VEC, bool BACKWARD>
+// SCATTER_TMA: the gradient row dO*W_ho (identical for every gene of the window) is staged once in
+// shared memory and added into g_ih[gene,:] with one TMA bulk reduction per gene
+// (cp.reduce.async.bulk.global.shared::cta.add.f32, D*4 bytes, SASS UBLKRED) instead of 32 lanes x
+// red.global.add.v4.f32: the scatter leaves the LSU/L1TEX path, which bounds the L2-resident configs.
+// GATHER_TMA: embedding rows are staged through shared memory with TMA bulk copies
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx, SASS UBLKCP), 2 stages of 2 KB per warp,
+// one lane issuing one row; the lanes then sum the rows with LDS.128 instead of LDG.128.
+template <int VEC, bool BACKWARD, bool SCATTER_TMA, bool GATHER_TMA>
 __global__ void __launch_bounds__(kCbowWarps * 32)
 cbow_rows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ gene,
                  const uint8_t *__restrict__ label, const int32_t *__restrict__ win,
@@ -51,11 +62,24 @@ cbow_rows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
     constexpr int D4 = D / 4;
     constexpr int UNR = 8 / VEC;                 // 8 float4 (128 B) in flight per lane
     __shared__ float sh_gho[BACKWARD ? D : 1];
+    // scatter staging row: its own buffer, or (both TMA paths on) stage 0 of the gather tile
+    __shared__ __align__(128) float sh_row[(BACKWARD && SCATTER_TMA && !GATHER_TMA) ? kCbowWarps * D : 4];
     __shared__ CtaAcc sh_acc;
+    constexpr int R = 4 / VEC;                   // rows per TMA stage (2 KB per warp per stage)
+    __shared__ __align__(128) float sh_tile[GATHER_TMA ? kCbowWarps * 2 * R * D : 4];
+    __shared__ __align__(8) unsigned long long sh_bar[GATHER_TMA ? kCbowWarps * 2 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (BACKWARD) for (int i = threadIdx.x; i < D; i += blockDim.x) sh_gho[i] = 0.f;
     if (threadIdx.x == 0) { sh_acc.loss = 0.0; sh_acc.correct = 0ull; }
+    if (GATHER_TMA) {
+        if (lane < 2) {
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&sh_bar[warp * 2 + lane]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    uint32_t tma_phase = 0;                      // bit s = parity of stage s
 
     const float4 *__restrict__ W4 = reinterpret_cast<const float4 *>(W_ih);
     float4 who[VEC], gho[VEC];
@@ -77,6 +101,57 @@ cbow_rows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
         for (int v = 0; v < VEC; ++v) h[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
         // ---- gather + segmented sum
+        if (GATHER_TMA) {
+            float *tile = sh_tile + (size_t)warp * 2 * R * D;
+            if (BACKWARD && SCATTER_TMA) {        // stage 0 doubles as the scatter staging row: drain its readers
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+            const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&sh_bar[warp * 2]);
+            const int nchunk = (e - b + R - 1) / R;
+            auto issue = [&](int c) {             // chunk c -> stage c & 1: lane r copies row r
+                const int st = c & 1;
+                const int32_t j = b + c * R + lane;
+                const int cnt = min(R, e - (b + c * R));
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + st * 8),
+                                 "r"(cnt * D * 4)
+                                 : "memory");
+                if (lane < cnt) {
+                    const float *src = W_ih + (size_t)__ldg(gene + j) * D;
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + (size_t)(st * R + lane) * D);
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                        "l"(src), "n"(D * 4), "r"(bar0 + st * 8)
+                        : "memory");
+                }
+            };
+            if (nchunk > 0) issue(0);
+            for (int c = 0; c < nchunk; ++c) {
+                const int st = c & 1;
+                if (c + 1 < nchunk) issue(c + 1);
+                const uint32_t par = (tma_phase >> st) & 1u;
+                uint32_t ok = 0;
+                while (!ok)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(ok)
+                                 : "r"(bar0 + st * 8), "r"(par)
+                                 : "memory");
+                tma_phase ^= (1u << st);
+                const int cnt = min(R, e - (b + c * R));
+                const float4 *t4 = reinterpret_cast<const float4 *>(tile + (size_t)st * R * D);
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (r < cnt) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            const float4 x = t4[r * D4 + v * 32 + lane];
+                            h[v].x += x.x; h[v].y += x.y; h[v].z += x.z; h[v].w += x.w;
+                        }
+                    }
+                __syncwarp();                     // stage st is free for chunk c + 2
+            }
+        } else
         for (int32_t base = b; base < e; base += 32) {
             const int cnt = min(32, e - base);
             const int32_t g = (lane < cnt) ? __ldg(gene + base + lane) : 0;
@@ -120,6 +195,24 @@ cbow_rows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
                 gv[v] = make_float4(who[v].x * s, who[v].y * s, who[v].z * s, who[v].w * s);
             }
             // ---- scatter-add the gradient rows
+            if (SCATTER_TMA) {
+                float *stage = GATHER_TMA ? sh_tile + (size_t)warp * 2 * R * D : sh_row + warp * D;
+                // the previous window's bulk reductions must have finished READING the staging row
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) reinterpret_cast<float4 *>(stage)[v * 32 + lane] = gv[v];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+                __syncwarp();
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
+                for (int32_t j = b + lane; j < e; j += 32) {
+                    float *dst = g_ih + (size_t)__ldg(gene + j) * D;
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                 ::"l"(dst), "r"(src), "n"(D * 4)
+                                 : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            } else
             for (int32_t base = b; base < e; base += 32) {
                 const int cnt = min(32, e - base);
                 const int32_t g = (lane < cnt) ? __ldg(gene + base + lane) : 0;
@@ -132,6 +225,8 @@ cbow_rows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
             }
         }
     }
+
+    if (BACKWARD && SCATTER_TMA) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
     // ---- CTA-level reduction of g_ho / loss / correct, then one global atomic each
     if (BACKWARD) {
@@ -285,10 +380,20 @@ static int launch_rows(const int32_t *rowptr, const int32_t *gene, const uint8_t
                        int32_t reduce, cudaStream_t st) {
     unsigned long long *nc = reinterpret_cast<unsigned long long *>(n_correct);
     int grid = 0, rc;
+    // scatter path of the backward kernel: "red" (red.global.add.v4.f32 per lane) or "tma"
+    // (cp.reduce.async.bulk per gene row); G2V_CBOW_SCATTER overrides the default
+    const char *sc = getenv("G2V_CBOW_SCATTER");
+    const bool tma = BACKWARD && (sc ? sc[0] == 't' : kDefaultScatterTma);
+    const char *gc = getenv("G2V_CBOW_GATHER");       // "ldg" (LDG.128 per lane) or "tma" (bulk copies via smem)
+    const bool gtma = gc ? gc[0] == 't' : kDefaultGatherTma;
 #define G2V_LAUNCH_VEC(VEC)                                                                          \
     {                                                                                                \
-        if ((rc = rows_grid((const void *)cbow_rows_kernel<VEC, BACKWARD>, 0, n_win, &grid))) return rc; \
-        cbow_rows_kernel<VEC, BACKWARD><<<grid, kCbowWarps * 32, 0, st>>>(                           \
+        auto kern = tma ? (gtma ? cbow_rows_kernel<VEC, BACKWARD, BACKWARD, true>                    \
+                                : cbow_rows_kernel<VEC, BACKWARD, BACKWARD, false>)                  \
+                        : (gtma ? cbow_rows_kernel<VEC, BACKWARD, false, true>                       \
+                                : cbow_rows_kernel<VEC, BACKWARD, false, false>);                    \
+        if ((rc = rows_grid((const void *)kern, 0, n_win, &grid))) return rc;                        \
+        kern<<<grid, kCbowWarps * 32, 0, st>>>(                                                      \
             rowptr, gene, label, win, win_begin, n_win, inv_n, W_ih, W_ho, g_ih, g_ho, loss_sum, nc, reduce); \
     }
     if (D == 128) G2V_LAUNCH_VEC(1)

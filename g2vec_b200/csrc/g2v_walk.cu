@@ -48,7 +48,11 @@ __device__ __forceinline__ bool visited(const int32_t *__restrict__ hs, uint32_t
     }
 }
 
-template <bool BITMAP>
+// One TILE of lanes (8, 16 or 32) per walker, 32/TILE walkers per warp.  The loop is a flat state
+// machine -- every iteration is "one step for every tile of the warp" -- so that tiles whose walkers end
+// at different times stay converged: finishing a walk (row write-out, visited-set reset) and fetching
+// the next ticket are short predicated sections of the same iteration.
+template <bool BITMAP, int TILE>
 __global__ void __launch_bounds__(kWalkWarps * 32)
 walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             const uint32_t *__restrict__ qw, int32_t V, int32_t L, int32_t Lpad, int32_t H,
@@ -56,135 +60,167 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             int64_t n_walkers, int64_t walker_stride, int32_t *__restrict__ out_nodes,
             int32_t *__restrict__ out_len, unsigned long long *__restrict__ ticket) {
     extern __shared__ int32_t smem[];
+    constexpr int NT = 32 / TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t *path = smem + (size_t)warp * (Lpad + H);
+    const int tile = lane / TILE, tl = lane % TILE, tbase = tile * TILE;
+    const unsigned tmask = TILE == 32 ? 0xffffffffu : (((1u << TILE) - 1u) << tbase);
+    int32_t *path = smem + (size_t)(warp * NT + tile) * (Lpad + H);
     int32_t *hs = path + Lpad;
     const uint32_t hmask = (uint32_t)H - 1u;
 
-    for (int i = lane; i < H; i += 32) hs[i] = BITMAP ? 0 : -1;
-    __syncwarp();
+    for (int i = tl; i < H; i += TILE) hs[i] = BITMAP ? 0 : -1;
+    __syncwarp(tmask);
+
+    bool have = false, done = false, dirty = false;
+    unsigned long long t = 0;
+    uint64_t subseq = 0;
+    int32_t cur = 0, n = 0, s = 0, dbase = -1;
+    uint32_t dlo = 0, dhi = 0;                           // lane tl holds the draw of step dbase + tl
 
     while (true) {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(ticket, 1ull);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if ((int64_t)t >= n_walkers) break;
-        const int64_t w = walker_begin + (int64_t)t * walker_stride;
-        const uint64_t subseq = ((uint64_t)group << 40) + (uint64_t)w;
-        int32_t cur = (int32_t)(w % V);
-        int32_t n = 0;
-        bool dirty = false;
-        uint32_t dlo = 0, dhi = 0;                       // lane k holds the draw of step (s & ~31) + k
-        int32_t dbase = -1;
+        if (!have && !done) {                            // take the next walker
+            unsigned long long tk = 0;
+            if (tl == 0) tk = atomicAdd(ticket, 1ull);
+            tk = __shfl_sync(tmask, tk, tbase);
+            if ((int64_t)tk >= n_walkers) {
+                done = true;
+            } else {
+                t = tk;
+                const int64_t w = walker_begin + (int64_t)tk * walker_stride;
+                subseq = ((uint64_t)group << 40) + (uint64_t)w;
+                cur = (int32_t)(w % V);
+                n = 0; s = 0; dbase = -1; dirty = false; have = true;
+            }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+        if (!have) continue;
 
-        for (int32_t s = 0; s < L; ++s) {
-            path[n] = cur;                               // every lane stores the same value: no divergence
-            ++n;
-            if (s == L - 1) break;                       // last draw is never appended
-            const int32_t b = __ldg(rowptr + cur), e = __ldg(rowptr + cur + 1);
-            if (b == e) break;                           // no out-edges: dead end
-            if (BITMAP) {                                // visited.insert(cur), uniform across the warp
+        // ---------------------------------------------------------------- one step of this tile's walker
+        path[n] = cur;                                   // every lane of the tile stores the same value
+        ++n;
+        bool end = (s == L - 1);                         // the L-th node is appended, never expanded
+        int32_t b = 0, e = 0;
+        if (!end) {
+            b = __ldg(rowptr + cur); e = __ldg(rowptr + cur + 1);
+            end = (b == e);                              // no out-edges: dead end
+        }
+        if (!end) {
+            if (BITMAP) {                                // visited.insert(cur), uniform across the tile
                 const int32_t wv = hs[cur >> 5];
-                __syncwarp();
+                __syncwarp(tmask);
                 hs[cur >> 5] = wv | (1 << (cur & 31));
             } else {
                 uint32_t i = hash_slot(cur, hshift);
                 while (hs[i] >= 0) i = (i + 1) & hmask;
-                __syncwarp();
+                __syncwarp(tmask);
                 hs[i] = cur;
             }
             dirty = true;
-            __syncwarp();
+            __syncwarp(tmask);
 
-            // ---- pass 1: weight of the unvisited out-neighbours, per chunk of 32 (REDUX.SUM)
+            // ---- pass 1: weight of the unvisited out-neighbours, per chunk of TILE (REDUX.SUM)
             uint32_t mq[kKC], tot[kKC];
             int32_t mc[kKC];
             unsigned long long T = 0;
 #pragma unroll
             for (int k = 0; k < kKC; ++k) {
                 mq[k] = 0; mc[k] = -1; tot[k] = 0;
-                if (b + k * 32 < e) {                    // warp-uniform
-                    const int32_t j = b + k * 32 + lane;
+                if (b + k * TILE < e) {                  // tile-uniform
+                    const int32_t j = b + k * TILE + tl;
                     if (j < e) {
                         const int32_t c = __ldg(col + j);
                         const uint32_t q = __ldg(qw + j);
                         mc[k] = c;
                         mq[k] = visited<BITMAP>(hs, hmask, hshift, c) ? 0u : q;
                     }
-                    tot[k] = __reduce_add_sync(0xffffffffu, mq[k]);   // <= 32 * 2^24
+                    tot[k] = __reduce_add_sync(tmask, mq[k]);         // <= 32 * 2^24
                     T += tot[k];
                 }
             }
-            for (int32_t jb = b + kKC * 32; jb < e; jb += 32) {       // rows longer than 128 neighbours
-                const int32_t j = jb + lane;
+            for (int32_t jb = b + kKC * TILE; jb < e; jb += TILE) {   // rows longer than kKC*TILE neighbours
+                const int32_t j = jb + tl;
                 uint32_t q = 0;
                 if (j < e) q = visited<BITMAP>(hs, hmask, hshift, __ldg(col + j)) ? 0u : __ldg(qw + j);
-                T += __reduce_add_sync(0xffffffffu, q);
+                T += __reduce_add_sync(tmask, q);
             }
-            if (T == 0) break;                           // every neighbour already visited
+            if (T == 0) {
+                end = true;                              // every neighbour already visited
+            } else {
+                // ---- one 64-bit Philox draw per step, r uniform in [0, T); TILE steps are drawn at once,
+                //      one per lane (counter-based: lane tl evaluates step dbase + tl)
+                if ((s / TILE) * TILE != dbase) {
+                    dbase = (s / TILE) * TILE;
+                    const uint64_t d = draw64(seed, subseq, (uint32_t)(dbase + tl));
+                    dlo = (uint32_t)d; dhi = (uint32_t)(d >> 32);
+                }
+                const int src = tbase + (s % TILE);
+                const uint64_t x = ((uint64_t)__shfl_sync(tmask, dhi, src) << 32) | __shfl_sync(tmask, dlo, src);
+                unsigned long long rem = __umul64hi(x, T);   // r - (weight of the chunks already skipped)
 
-            // ---- one 64-bit Philox draw per step, r uniform in [0, T); 32 steps are drawn at once,
-            //      one per lane (counter-based: lane k evaluates step dbase + k)
-            if ((s & ~31) != dbase) {
-                dbase = s & ~31;
-                const uint64_t d = draw64(seed, subseq, (uint32_t)(dbase + lane));
-                dlo = (uint32_t)d; dhi = (uint32_t)(d >> 32);
-            }
-            const uint64_t x = ((uint64_t)__shfl_sync(0xffffffffu, dhi, s & 31) << 32) |
-                               __shfl_sync(0xffffffffu, dlo, s & 31);
-            unsigned long long rem = __umul64hi(x, T);   // r - (weight of the chunks already skipped)
-
-            // ---- pass 2: chunk that contains r (uniform scalar search), then one warp scan inside it
-            int32_t nxt = -1;
-            bool found = false;
+                // ---- pass 2: chunk that contains r (tile-uniform scalar search), then one scan inside it
+                int32_t nxt = -1;
+                bool found = false;
 #pragma unroll
-            for (int k = 0; k < kKC; ++k) {
-                if (!found && b + k * 32 < e) {
-                    if (rem < (unsigned long long)tot[k]) {
-                        const uint32_t incl = warp_inclusive_scan_u32(mq[k], lane);
-                        const unsigned hit = __ballot_sync(0xffffffffu, incl > (uint32_t)rem);
-                        nxt = __shfl_sync(0xffffffffu, mc[k], __ffs(hit) - 1);
-                        found = true;
-                    } else {
-                        rem -= tot[k];
+                for (int k = 0; k < kKC; ++k) {
+                    if (!found && b + k * TILE < e) {
+                        if (rem < (unsigned long long)tot[k]) {
+                            uint32_t incl = mq[k];
+#pragma unroll
+                            for (int o = 1; o < TILE; o <<= 1) {
+                                const uint32_t up = __shfl_up_sync(tmask, incl, o, TILE);
+                                if (tl >= o) incl += up;
+                            }
+                            const unsigned hit = __ballot_sync(tmask, incl > (uint32_t)rem);
+                            nxt = __shfl_sync(tmask, mc[k], __ffs(hit) - 1);
+                            found = true;
+                        } else {
+                            rem -= tot[k];
+                        }
                     }
                 }
-            }
-            for (int32_t jb = b + kKC * 32; !found && jb < e; jb += 32) {
-                const int32_t j = jb + lane;
-                int32_t c = -1;
-                uint32_t q = 0;
-                if (j < e) {
-                    c = __ldg(col + j);
-                    q = visited<BITMAP>(hs, hmask, hshift, c) ? 0u : __ldg(qw + j);
+                for (int32_t jb = b + kKC * TILE; !found && jb < e; jb += TILE) {
+                    const int32_t j = jb + tl;
+                    int32_t c = -1;
+                    uint32_t q = 0;
+                    if (j < e) {
+                        c = __ldg(col + j);
+                        q = visited<BITMAP>(hs, hmask, hshift, c) ? 0u : __ldg(qw + j);
+                    }
+                    const uint32_t ct = __reduce_add_sync(tmask, q);
+                    if (rem < (unsigned long long)ct) {
+                        uint32_t incl = q;
+#pragma unroll
+                        for (int o = 1; o < TILE; o <<= 1) {
+                            const uint32_t up = __shfl_up_sync(tmask, incl, o, TILE);
+                            if (tl >= o) incl += up;
+                        }
+                        const unsigned hit = __ballot_sync(tmask, incl > (uint32_t)rem);
+                        nxt = __shfl_sync(tmask, c, __ffs(hit) - 1);
+                        found = true;
+                    } else {
+                        rem -= ct;
+                    }
                 }
-                const uint32_t ct = __reduce_add_sync(0xffffffffu, q);
-                if (rem < (unsigned long long)ct) {
-                    const uint32_t incl = warp_inclusive_scan_u32(q, lane);
-                    const unsigned hit = __ballot_sync(0xffffffffu, incl > (uint32_t)rem);
-                    nxt = __shfl_sync(0xffffffffu, c, __ffs(hit) - 1);
-                    found = true;
+                cur = nxt;
+                ++s;
+            }
+        }
+        if (end) {                                       // walk finished: write the row once, coalesced
+            __syncwarp(tmask);
+            int32_t *row = out_nodes + (size_t)t * (size_t)L;
+            for (int i = tl; i < L; i += TILE) row[i] = (i < n) ? path[i] : -1;
+            if (tl == 0) out_len[t] = n;
+            if (dirty) {
+                __syncwarp(tmask);
+                if (BITMAP) {
+                    for (int i = tl; i < n; i += TILE) hs[path[i] >> 5] = 0;   // only the words this walk touched
                 } else {
-                    rem -= ct;
+                    for (int i = tl; i < H; i += TILE) hs[i] = -1;
                 }
             }
-            cur = nxt;
+            __syncwarp(tmask);
+            have = false;
         }
-
-        __syncwarp();
-        // ---- write the row once, coalesced; -1 padding
-        int32_t *row = out_nodes + (size_t)t * (size_t)L;
-        for (int i = lane; i < L; i += 32) row[i] = (i < n) ? path[i] : -1;
-        if (lane == 0) out_len[t] = n;
-        if (dirty) {
-            __syncwarp();
-            if (BITMAP) {
-                for (int i = lane; i < n; i += 32) hs[path[i] >> 5] = 0;   // only the words this walk touched
-            } else {
-                for (int i = lane; i < H; i += 32) hs[i] = -1;
-            }
-        }
-        __syncwarp();
     }
 }
 
@@ -216,11 +252,17 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
     if (device_props(&dp)) return 1;
     G2V_REQUIRE(dp.cc_major == 10, "g2v_walk_launch: needs an sm_100 device (found sm_%d%d)", dp.cc_major, dp.cc_minor);
 
-    // visited set per warp: a V-bit bitmap when it is small enough to keep >= 4 CTAs per SM, else a hash set
+    // lanes per walker from the mean out-degree (a chunk of TILE neighbours per load; 4 chunks are cached)
+    const char *ft = getenv("G2V_WALK_TILE");                     // test hook: 8 / 16 / 32
+    const double mean_deg = (double)E / (double)V;
+    int tile = mean_deg <= 12.0 ? 8 : (mean_deg <= 56.0 ? 16 : 32);
+    if (ft && (atoi(ft) == 8 || atoi(ft) == 16 || atoi(ft) == 32)) tile = atoi(ft);
+    const int nt = 32 / tile;
+    // visited set per walker: a V-bit bitmap when a CTA's bitmaps fit 56 KB (>= 4 CTAs per SM), else a hash set
     const int Lpad = (L + 31) & ~31;
     const int bm_words = (V + 31) / 32;
-    const char *force = getenv("G2V_WALK_VISITED");             // test hook: "hash" / "bitmap"
-    bool bitmap = (size_t)kWalkWarps * (Lpad + bm_words) * sizeof(int32_t) <= 56 * 1024;
+    const char *force = getenv("G2V_WALK_VISITED");               // test hook: "hash" / "bitmap"
+    bool bitmap = (size_t)kWalkWarps * nt * (Lpad + bm_words) * sizeof(int32_t) <= 56 * 1024;
     if (force && force[0] == 'h') bitmap = false;
     int H = 64, hshift = 26;
     if (bitmap) {
@@ -228,21 +270,27 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
     } else {
         while (H < 3 * L) { H <<= 1; --hshift; }
     }
-    const size_t smem = (size_t)kWalkWarps * (Lpad + H) * sizeof(int32_t);
+    const size_t smem = (size_t)kWalkWarps * nt * (Lpad + H) * sizeof(int32_t);
     G2V_REQUIRE(smem <= (size_t)dp.max_smem_optin, "g2v_walk_launch: lenPath %d needs %zu B of shared memory", L, smem);
     cudaStream_t st = (cudaStream_t)stream;
-    auto kern = bitmap ? walk_kernel<true> : walk_kernel<false>;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[bitmap]) {
+    typedef void (*kern_t)(const int32_t *, const int32_t *, const uint32_t *, int32_t, int32_t, int32_t, int32_t,
+                           int32_t, uint64_t, uint32_t, int64_t, int64_t, int64_t, int32_t *, int32_t *,
+                           unsigned long long *);
+    static const kern_t table[2][3] = {{walk_kernel<false, 8>, walk_kernel<false, 16>, walk_kernel<false, 32>},
+                                       {walk_kernel<true, 8>, walk_kernel<true, 16>, walk_kernel<true, 32>}};
+    const int ti = tile == 8 ? 0 : (tile == 16 ? 1 : 2);
+    kern_t kern = table[bitmap][ti];
+    static bool attr_done[2][3] = {{false, false, false}, {false, false, false}};
+    if (!attr_done[bitmap][ti]) {
         G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
         G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_done[bitmap] = true;
+        attr_done[bitmap][ti] = true;
     }
     int per_sm = 0;
     G2V_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWalkWarps * 32, smem));
     G2V_REQUIRE(per_sm > 0, "g2v_walk_launch: kernel does not fit on an SM");
     int64_t grid = (int64_t)dp.sm_count * per_sm;                 // persistent: whole chip resident
-    const int64_t need = (n_walkers + kWalkWarps - 1) / kWalkWarps;
+    const int64_t need = (n_walkers + kWalkWarps * nt - 1) / (kWalkWarps * nt);
     if (grid > need) grid = need;
     G2V_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(unsigned long long), st));
     kern<<<(unsigned)grid, kWalkWarps * 32, smem, st>>>(

@@ -127,6 +127,34 @@ def test_ex_windows_five_steps_match_oracle(g2v):
     assert (got[~touched] == W0[~touched]).all() and (~touched).sum() > 1000
 
 
+def test_config1_parity_run_ten_repetitions(g2v):
+    """ex_* graphs, -p 80 -s 128 -e 5, numRepetition 10, lr 0.005: windows from the
+    GPU sampler equal the oracle's (bit-exact walks -> identical path sets), vectors within 1e-4."""
+    import g2vec_b200
+    from g2vec_b200 import paths
+    (rowptr, gene, label), o_rows = helpers.ex_windows(reps=10)
+    rows = []
+    for grp in (0, 1):
+        rp, col, w = helpers.ex_graph(grp)
+        wg = g2vec_b200.WalkGraph(rp, col, weights=w)
+        nodes, lens = g2vec_b200.generate_paths(wg, 80, 10, seed=0, group=grp)
+        rows.append(paths.canonical_rows(nodes, lens))
+    prow, plab = paths.integrate(rows[0], rows[1])
+    g_rowptr, g_gene, g_label = paths.windows_csr(prow, plab)
+    N = len(rowptr) - 1
+    assert g_rowptr.shape[0] - 1 == N and 40000 < N < 50000          # README.md:31 reports 45402 (unseeded)
+    got_set = {(int(l), tuple(int(x) for x in r[r != paths.PAD])) for r, l in zip(prow.cpu().numpy(), plab.cpu().numpy())}
+    assert got_set == set(o_rows)
+    V, D = 7523, 128
+    tr, va = oracle.split_indices(N, 0)
+    W0, Wo0 = helpers.init_weights(V, D, 0)
+    want, hist, _, _ = oracle.cbow_train(rowptr, gene, label, tr, va, W0, Wo0, 0.005, max_steps=5, early_stop=False)
+    for algo in ("rows", "rank1"):
+        got = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=5, seed=0, W_ih0=W0, W_ho0=Wo0,
+                             early_stop=False, log=None, algo=algo)
+        assert rel_max(got, want) < RTOL_VEC, algo
+
+
 def test_ex_windows_early_stop_run(g2v):
     """Full reference loop with early stopping; the stop step depends on exact accuracy comparisons
     (G2Vec.py:276), so it is reported with a tolerance of one step; vectors are compared at the oracle's
@@ -223,3 +251,57 @@ def test_rank1_ex_windows_five_steps_match_oracle(g2v):
     rows, _ = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=5, seed=0, W_ih0=W0, W_ho0=Wo0,
                              early_stop=False, log=None, return_info=True, algo="rows")
     assert rel_max(got, rows) < RTOL_VEC
+
+
+def test_minibatch_variant_and_dense_adapter(g2v):
+    """north_star's mini-batch variant (one optimizer step per batch) against an oracle loop; batch >= N is
+    the reference's full batch; and the reference-shaped adapter compute_genetovec(dense pathList, ...)."""
+    V, N, D = 300, 1200, 128
+    rowptr, gene, label = helpers.random_windows(N, V, 1, 30, seed=12)
+    W0, Wo0 = helpers.init_weights(V, D, 2)
+    tr, va = oracle.split_indices(N, 0)
+    B = 256
+    W, Wo = W0.copy(), Wo0.copy()
+    st = [np.zeros_like(W), np.zeros_like(W), np.zeros_like(Wo), np.zeros_like(Wo)]
+    t = 0
+    for epoch in range(2):
+        for lo in range(0, len(tr), B):
+            sub = tr[lo:lo + B]
+            g_ih, g_ho, _, _ = oracle.cbow_grad(rowptr, gene, label, sub, len(sub), W, Wo)
+            t += 1
+            oracle.adam_(W, st[0], st[1], g_ih, 0.005, t); oracle.adam_(Wo, st[2], st[3], g_ho, 0.005, t)
+    for algo in ("rows", "rank1"):
+        got = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=2, seed=0, W_ih0=W0, W_ho0=Wo0,
+                             early_stop=False, log=None, batch=B, algo=algo)
+        assert rel_max(got, W) < RTOL_VEC, algo
+    full = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=3, seed=0, W_ih0=W0, W_ho0=Wo0,
+                          early_stop=False, log=None)
+    big = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=3, seed=0, W_ih0=W0, W_ho0=Wo0,
+                         early_stop=False, log=None, batch=10 * N)
+    assert rel_max(big, full) < 1e-5
+    # dense adapter: pathList [N, V+1] as integrate_pathSet builds it (G2Vec.py:316-320)
+    P = np.zeros((N, V + 1), dtype=np.int32)
+    for n in range(N):
+        P[n, gene[rowptr[n]:rowptr[n + 1]]] = 1
+    P[:, -1] = label
+    lines = []
+    a = g2v.compute_genetovec(P, V, D, 0.005, max_epoch=3, seed=0, log=lines.append)
+    b = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=3, seed=0, log=None)
+    assert a.shape == (V, D) and a.dtype == np.float32 and rel_max(a, b) < 1e-5
+    assert lines[0].strip() == "Start training the modified CBOW with early stopping"
+
+
+@pytest.mark.parametrize("gather,scatter", [("tma", "red"), ("ldg", "tma"), ("tma", "tma")])
+@pytest.mark.parametrize("D", [128, 256, 512])
+def test_tma_staged_variants_equal_oracle(g2v, monkeypatch, gather, scatter, D):
+    """The TMA-staged forms of the fused kernel (bulk-copy gather through shared memory, bulk-reduce
+    scatter) compute the same step; which one ships is decided by measurement (profiles/README.md)."""
+    monkeypatch.setenv("G2V_CBOW_GATHER", gather)
+    monkeypatch.setenv("G2V_CBOW_SCATTER", scatter)
+    V, N = 400, 2500
+    rowptr, gene, label = helpers.random_windows(N, V, 1, 80, seed=D + 7)
+    m, W0, Wo0, g_ih, g_ho, loss, nc = one_step(g2v, rowptr, gene, label, V, D)
+    win = np.arange(N, dtype=np.int64)
+    o_gih, o_gho, o_loss, o_nc = oracle.cbow_grad(rowptr, gene, label, win, N, W0, Wo0)
+    assert rel_max(g_ih, o_gih) < 2e-5 and rel_max(g_ho, o_gho) < 2e-5
+    assert abs(loss / N - o_loss) < 1e-5 * max(1.0, abs(o_loss)) and abs(nc - o_nc) <= 2

@@ -151,3 +151,23 @@ def test_hash_visited_set_path(g2v, monkeypatch):
     want, wl = oracle.walks(rp, col, q, 80, 5, 1, 0, 120_000)
     got, gl = run_gpu(g2v, rp, col, q, 80, 1, 5, 1)
     assert (got == want).all() and (gl == wl).all() and wl.max() == 80 and wl.min() == 1
+
+
+@pytest.mark.parametrize("tile", ["8", "16", "32"])
+@pytest.mark.parametrize("vis", ["bitmap", "hash"])
+def test_every_tile_width_and_visited_set_is_bit_exact(g2v, monkeypatch, tile, vis):
+    """8/16/32 lanes per walker (chosen from the mean degree in production) x bitmap/hash visited set."""
+    monkeypatch.setenv("G2V_WALK_TILE", tile)
+    monkeypatch.setenv("G2V_WALK_VISITED", vis)
+    cases = [helpers.ex_graph(1) + (80, 2), helpers.random_graph(2000, 40, seed=1, dead_frac=0.2) + (33, 3)]
+    V = 300
+    A = (0.5 + 0.5 * np.random.RandomState(4).rand(V, V)).astype(np.float32) + np.float32(1e-4)
+    np.fill_diagonal(A, 0)
+    from oracle import legacy
+    cases.append(legacy.csr_from_dense(A) + (300, 1))            # rows of 299 neighbours: tail path at every width
+    for rp, col, w, L, reps in cases:
+        q = oracle.quantise_weights(w)
+        n = len(rp) - 1
+        want, wl = oracle.walks(rp, col, q, L, 77, 1, 0, reps * n)
+        got, gl = run_gpu(g2v, rp, col, q, L, reps, 77, 1)
+        assert (gl == wl).all() and (got == want).all()
