@@ -349,6 +349,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, walk_cpu = cpu_baseline(args, gs, V, D, L, rowptr.cpu().numpy(), gene.cpu().numpy(), label.cpu().numpy())
 
+    walkers_total = int(allsum(2 * n_walk))
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -378,7 +379,7 @@ def run_b200(args):
                         "reassociation; rows = north_star's embedding-row gather/scatter kernel"},
             "cpu_baseline": cpu,
             "walk": {"metric": "random_walk_steps_per_sec", "value": visits / (walk_ms * 1e-3), "unit": "steps/s",
-                     "ms_per_pass": walk_ms, "walkers": int(allsum(2 * n_walk)) if world > 1 else 2 * n_walk,
+                     "ms_per_pass": walk_ms, "walkers": walkers_total,
                      "visits_per_pass": visits,
                      "roofline": {"kernel": "walk_kernel", "bound": "hbm", "achieved": walk_gbs, "peak": peak,
                                   "unit": "GB/s", "frac": walk_gbs / peak,

@@ -76,7 +76,11 @@ def test_command_line_end_to_end(tmp_path, golden_dir, capsys):
     with open(nf, "w") as f:
         f.write("src\tdest\n")
         f.writelines("%s\t%s\n" % (genes[a], genes[b]) for a, b in zip(e["src"], e["dst"]))
-        f.write("%s\tNOT_IN_EXPRESSION\n" % genes[0])                                  # dropped by step 2
+        # genes whose only network partners are outside the expression data: present in the network's gene
+        # set (so they stay in the common gene list, 7523) while the edge itself is dropped by step 2
+        seen = np.zeros(len(genes), bool); seen[e["src"]] = True; seen[e["dst"]] = True
+        f.writelines("%s\tNOT_IN_EXPRESSION\n" % g for g in genes[~seen])
+        f.write("%s\tNOT_IN_EXPRESSION\n" % genes[0])
     outs = []
     for run in range(2):
         prefix = str(tmp_path / ("res%d" % run))
