@@ -32,6 +32,8 @@ SIGNATURES = {
                                           _i32, _i32, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
     "g2v_cbow_r1_prepare": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "g2v_cbow_r1_windows": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "g2v_cbow_r1_windows_csc": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                              _i32, _i32, _vp]),
     "g2v_cbow_r1_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32,
                                          _f32, _f32, _i32, _vp]),
     "g2v_pcc_zscore": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp]),

@@ -101,6 +101,26 @@ class CbowModel:
             _capi.check(self.lib.g2v_cbow_r1_prepare(self.W_ih.data_ptr(), self.W_ho.data_ptr(), self.s.data_ptr(),
                                                      self.V, self.D, self._stream()), "g2v_cbow_r1_prepare")
 
+    def prepare_csc(self, win):
+        """rank1 only: transpose the incidence of the window list ``win`` (int32 device tensor) once, so that
+        fwdbwd(win, ...) over the WHOLE list forms c without atomics (deterministic, and faster when few
+        genes receive many windows).  The windows are static across steps (full batch), so this is setup."""
+        if self.algo != "rank1":
+            return
+        w = win.to(torch.int64)
+        starts = self.rowptr[w].to(torch.int64)
+        lens = self.rowptr[w + 1].to(torch.int64) - starts
+        total = int(lens.sum())
+        pos = torch.repeat_interleave(torch.arange(w.shape[0], device=self.device), lens)
+        first = torch.cumsum(lens, 0) - lens
+        idx = starts[pos] + (torch.arange(total, device=self.device) - first[pos])
+        g = self.gene[idx].to(torch.int64)
+        g, order = torch.sort(g, stable=True)
+        cscptr = torch.zeros(self.V + 1, dtype=torch.int64, device=self.device)
+        cscptr[1:] = torch.cumsum(torch.bincount(g, minlength=self.V), 0)
+        self._csc = (win.data_ptr(), int(w.shape[0]), cscptr.to(torch.int32), pos[order].to(torch.int32),
+                     torch.empty(w.shape[0], dtype=torch.float32, device=self.device))
+
     def grad_tensors(self):
         """What a multi-GPU step must all-reduce (sum) between fwdbwd() and update()."""
         return [self.g_ih, self.g_ho] if self.algo == "rows" else [self.c]
@@ -117,6 +137,16 @@ class CbowModel:
         pre-update correct count -> acc[1])."""
         n = (win.shape[0] - win_begin) if n_win is None else n_win
         if self.algo == "rank1":
+            csc = getattr(self, "_csc", None)
+            if csc is not None and win is not None and csc[0] == win.data_ptr() and win_begin == 0 and n == csc[1]:
+                rc = self.lib.g2v_cbow_r1_windows_csc(self.rowptr.data_ptr(), self.gene.data_ptr(),
+                                                      self.label.data_ptr(), win.data_ptr(), int(n),
+                                                      1.0 / float(n_total), self.s.data_ptr(), csc[2].data_ptr(),
+                                                      csc[3].data_ptr(), csc[4].data_ptr(), self.c.data_ptr(),
+                                                      self.acc.data_ptr(), self.acc.data_ptr() + 8, self.V,
+                                                      self.reduce, self._stream())
+                _capi.check(rc, "g2v_cbow_r1_windows_csc")
+                return
             rc = self.lib.g2v_cbow_r1_windows(self.rowptr.data_ptr(), self.gene.data_ptr(), self.label.data_ptr(),
                                               self._ptr(win), int(win_begin), int(n), 1.0 / float(n_total),
                                               self.s.data_ptr(), self.c.data_ptr(), self.acc.data_ptr(),
@@ -203,6 +233,8 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
     tr_d = torch.from_numpy(np.ascontiguousarray(tr_loc, dtype=np.int32)).to(dev)
     va_d = torch.from_numpy(np.ascontiguousarray(va_loc, dtype=np.int32)).to(dev)
 
+    if algo == "rank1" and (batch <= 0 or batch >= n_tr) and len(tr_loc):
+        model.prepare_csc(tr_d)
     if log:
         log("     Start training the modified CBOW with early stopping")
     t0 = time.time()

@@ -63,13 +63,16 @@ r1_prepare_kernel(const float *__restrict__ W_ih, const float *__restrict__ W_ho
 // ---- per-window forward (+ backward into c) -------------------------------------------------------
 struct R1Acc { double loss; unsigned long long correct; };
 
-template <bool BACKWARD>
+// MODE 0: accuracy only.  MODE 1: backward with c[gene] += dO (scalar red).  MODE 2: backward that only
+// stores dO[i] for list position i; c is then formed without atomics by r1_csc_reduce_kernel.
+template <int MODE>
 __global__ void __launch_bounds__(kR1Warps * 32)
 r1_windows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ gene,
                   const uint8_t *__restrict__ label, const int32_t *__restrict__ win, int64_t win_begin,
                   int64_t n_win, float inv_n, const float *__restrict__ s, float *__restrict__ c,
                   double *__restrict__ loss_sum, unsigned long long *__restrict__ n_correct,
                   int32_t reduce_mean) {
+    constexpr bool BACKWARD = MODE != 0;
     __shared__ R1Acc sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { sh.loss = 0.0; sh.correct = 0ull; }
@@ -89,9 +92,11 @@ r1_windows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict_
             correct_acc += ((o > 0.f) == (y != 0.f)) ? 1u : 0u;
             if (BACKWARD) loss_acc += fmaxf(o, 0.f) - o * y + log1pf(expf(-fabsf(o)));
         }
-        if (BACKWARD) {
+        if (MODE == 1) {
             const float dO = (sigmoid_stable_r1(o) - y) * inv_n * scale;
             for (int32_t j = b + lane; j < e; j += 32) atomicAdd(c + __ldg(gene + j), dO);
+        } else if (MODE == 2) {
+            if (lane == 0) c[i] = (sigmoid_stable_r1(o) - y) * inv_n * scale;    // c is the dO array here
         }
     }
     if (lane == 0) {
@@ -102,6 +107,29 @@ r1_windows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict_
     if (threadIdx.x == 0) {
         if (BACKWARD && loss_sum) atomicAdd(loss_sum, sh.loss);
         if (n_correct) atomicAdd(n_correct, sh.correct);
+    }
+}
+
+// c[g] += sum over the list positions whose window contains g of dO[pos]: one warp per gene, fixed lane
+// assignment and shuffle tree => bit-reproducible from run to run (no floating-point atomics).
+__global__ void __launch_bounds__(kR1Warps * 32)
+r1_csc_reduce_kernel(const int32_t *__restrict__ cscptr, const int32_t *__restrict__ csc_pos,
+                     const float *__restrict__ dO, float *__restrict__ c, int32_t V) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kR1Warps + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * kR1Warps;
+    for (int64_t g = warp; g < V; g += nwarps) {
+        const int32_t b = __ldg(cscptr + g), e = __ldg(cscptr + g + 1);
+        if (b == e) continue;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int32_t j = b + lane;
+        for (; j + 96 < e; j += 128) {
+            a0 += __ldg(dO + __ldg(csc_pos + j));      a1 += __ldg(dO + __ldg(csc_pos + j + 32));
+            a2 += __ldg(dO + __ldg(csc_pos + j + 64)); a3 += __ldg(dO + __ldg(csc_pos + j + 96));
+        }
+        for (; j < e; j += 32) a0 += __ldg(dO + __ldg(csc_pos + j));
+        const float tot = warp_sum((a0 + a1) + (a2 + a3));
+        if (lane == 0) c[g] += tot;
     }
 }
 
@@ -246,16 +274,39 @@ extern "C" int g2v_cbow_r1_windows(const int32_t *rowptr, const int32_t *gene, c
     int grid = 0, rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (c) {
-        if ((rc = r1_grid((const void *)r1_windows_kernel<true>, 0, n_win, &grid))) return rc;
-        r1_windows_kernel<true><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, win_begin, n_win,
-                                                               inv_n_total, s, c, loss_sum, nc, reduce);
+        if ((rc = r1_grid((const void *)r1_windows_kernel<1>, 0, n_win, &grid))) return rc;
+        r1_windows_kernel<1><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, win_begin, n_win,
+                                                            inv_n_total, s, c, loss_sum, nc, reduce);
     } else {
-        if ((rc = r1_grid((const void *)r1_windows_kernel<false>, 0, n_win, &grid))) return rc;
-        r1_windows_kernel<false><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, win_begin, n_win, 0.f,
-                                                                s, nullptr, nullptr, nc, reduce);
+        if ((rc = r1_grid((const void *)r1_windows_kernel<0>, 0, n_win, &grid))) return rc;
+        r1_windows_kernel<0><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, win_begin, n_win, 0.f,
+                                                            s, nullptr, nullptr, nc, reduce);
     }
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
+    return 0;
+}
+
+extern "C" int g2v_cbow_r1_windows_csc(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
+                                       const int32_t *win, int64_t n_win, float inv_n_total, const float *s,
+                                       const int32_t *cscptr, const int32_t *csc_pos, float *dO, float *c,
+                                       double *loss_sum, int64_t *n_correct, int32_t V, int32_t reduce,
+                                       void *stream) {
+    G2V_REQUIRE(V > 0 && n_win >= 0, "g2v_cbow_r1_windows_csc: bad sizes");
+    G2V_REQUIRE(rowptr && label && s && cscptr && dO && c, "g2v_cbow_r1_windows_csc: null pointer");
+    G2V_REQUIRE(reduce == G2V_REDUCE_SUM || reduce == G2V_REDUCE_MEAN, "g2v_cbow_r1_windows_csc: unknown reduce %d", reduce);
+    if (n_win == 0) return 0;
+    unsigned long long *nc = reinterpret_cast<unsigned long long *>(n_correct);
+    int grid = 0, rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = r1_grid((const void *)r1_windows_kernel<2>, 0, n_win, &grid))) return rc;
+    r1_windows_kernel<2><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, 0, n_win, inv_n_total, s, dO,
+                                                        loss_sum, nc, reduce);
+    G2V_CUDA_OK(cudaGetLastError());
+    if ((rc = r1_grid((const void *)r1_csc_reduce_kernel, 0, V, &grid))) return rc;
+    r1_csc_reduce_kernel<<<grid, kR1Warps * 32, 0, st>>>(cscptr, csc_pos, dO, c, V);
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch(2);
     return 0;
 }
 

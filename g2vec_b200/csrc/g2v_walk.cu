@@ -92,8 +92,12 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                 n = 0; s = 0; dbase = -1; dirty = false; have = true;
             }
         }
-        if (__all_sync(0xffffffffu, done)) break;
-        if (!have) continue;
+        if (TILE == 32) {
+            if (done) break;                             // one walker per warp: nothing to wait for
+        } else {
+            if (__all_sync(0xffffffffu, done)) break;
+            if (!have) continue;
+        }
 
         // ---------------------------------------------------------------- one step of this tile's walker
         path[n] = cur;                                   // every lane of the tile stores the same value
@@ -255,7 +259,7 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
     // lanes per walker from the mean out-degree (a chunk of TILE neighbours per load; 4 chunks are cached)
     const char *ft = getenv("G2V_WALK_TILE");                     // test hook: 8 / 16 / 32
     const double mean_deg = (double)E / (double)V;
-    int tile = mean_deg <= 12.0 ? 8 : (mean_deg <= 56.0 ? 16 : 32);
+    int tile = mean_deg <= 6.0 ? 8 : (mean_deg <= 20.0 ? 16 : 32);   // measured: profiles/README.md
     if (ft && (atoi(ft) == 8 || atoi(ft) == 16 || atoi(ft) == 32)) tile = atoi(ft);
     const int nt = 32 / tile;
     // visited set per walker: a V-bit bitmap when a CTA's bitmaps fit 56 KB (>= 4 CTAs per SM), else a hash set

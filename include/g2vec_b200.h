@@ -140,6 +140,14 @@ int g2v_cbow_r1_windows(const int32_t *rowptr, const int32_t *gene, const uint8_
                         const int32_t *win, int64_t win_begin, int64_t n_win, float inv_n_total,
                         const float *s, float *c, double *loss_sum, int64_t *n_correct, int32_t V,
                         int32_t reduce, void *stream);
+/* Deterministic backward: the list's windows x genes incidence is also given transposed (CSC over list
+ * positions: cscptr [V+1], csc_pos [nnz] = positions i in 0..n_win-1 of the windows that contain the gene).
+ * dO [n_win] is scratch; c[g] += sum of dO over the gene's positions with a fixed reduction order, so
+ * the step is bit-reproducible (no floating-point atomics). */
+int g2v_cbow_r1_windows_csc(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
+                            const int32_t *win, int64_t n_win, float inv_n_total, const float *s,
+                            const int32_t *cscptr, const int32_t *csc_pos, float *dO, float *c,
+                            double *loss_sum, int64_t *n_correct, int32_t V, int32_t reduce, void *stream);
 int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
                        float *c, float *g_ho, float *s, int32_t V, int32_t D, int32_t optimizer,
                        float lr, float beta1, float beta2, float eps, int32_t t, void *stream);

@@ -305,3 +305,24 @@ def test_tma_staged_variants_equal_oracle(g2v, monkeypatch, gather, scatter, D):
     o_gih, o_gho, o_loss, o_nc = oracle.cbow_grad(rowptr, gene, label, win, N, W0, Wo0)
     assert rel_max(g_ih, o_gih) < 2e-5 and rel_max(g_ho, o_gho) < 2e-5
     assert abs(loss / N - o_loss) < 1e-5 * max(1.0, abs(o_loss)) and abs(nc - o_nc) <= 2
+
+
+def test_rank1_csc_backward_is_bit_reproducible(g2v):
+    """With the transposed incidence (CSC) the collapsed trainer has no floating-point atomics: two runs
+    give bit-identical vectors (the row formulation, with red.global.add, does not promise that)."""
+    (rowptr, gene, label), _ = helpers.ex_windows(reps=2)
+    V, D = 7523, 128
+    W0, Wo0 = helpers.init_weights(V, D, 0)
+    runs = [g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=6, seed=0, W_ih0=W0, W_ho0=Wo0,
+                           early_stop=False, log=None, algo="rank1") for _ in range(2)]
+    assert (runs[0] == runs[1]).all()
+    # and it equals the atomics form of the same algorithm to reassociation
+    import torch
+    N = len(rowptr) - 1
+    m = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, algo="rank1")
+    win = torch.arange(N, dtype=torch.int32, device="cuda")
+    m.fwdbwd(win, N); torch.cuda.synchronize()
+    c_atomic = m.c.cpu().numpy().copy(); m.c.zero_()
+    m.prepare_csc(win); m.fwdbwd(win, N); torch.cuda.synchronize()
+    c_csc = m.c.cpu().numpy()
+    assert np.abs(c_csc - c_atomic).max() <= 1e-5 * np.abs(c_atomic).max()
