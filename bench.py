@@ -325,22 +325,45 @@ def run_b200(args):
 
     e2e = None
     if not args.no_e2e:
+        # Every step's windows come from pinned host memory.  The upload of step k+1 runs on a copy stream
+        # into the other of two device buffer sets while step k computes (input double-buffering); the timed
+        # region contains every copy and the per-step device->host read of the accuracies.
         pins = [t.cpu().pin_memory() for t in (model.rowptr, model.gene, model.label)]
-        def e2e_step():
-            model.rowptr.copy_(pins[0], non_blocking=True); model.gene.copy_(pins[1], non_blocking=True)
-            model.label.copy_(pins[2], non_blocking=True)
-            cbow_step()
-            torch.cuda.current_stream().synchronize()
-        e2e_step()
+        bufs = [[model.rowptr, model.gene, model.label], [torch.empty_like(t) for t in (model.rowptr, model.gene, model.label)]]
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def upload(k):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[k])                # the step that last read this buffer set is done
+                for d_, h_ in zip(bufs[k], pins):
+                    d_.copy_(h_, non_blocking=True)
+                ready[k].record(copy_stream)
+
+        def e2e_run(n):
+            for k in (0, 1):
+                freed[k].record(torch.cuda.current_stream())
+            upload(0)
+            for i in range(n):
+                k = i & 1
+                if i + 1 < n:
+                    upload(k ^ 1)
+                torch.cuda.current_stream().wait_event(ready[k])
+                model.rowptr, model.gene, model.label = bufs[k]
+                cbow_step()
+                freed[k].record(torch.cuda.current_stream())
+                torch.cuda.current_stream().synchronize()       # the accuracies are on the host
+        e2e_run(2)
         barrier(); t0 = time.perf_counter()
-        for _ in range(K):
-            e2e_step()
+        e2e_run(K)
         barrier(); dt = allmax((time.perf_counter() - t0) / K)
+        model.rowptr, model.gene, model.label = bufs[0]
         e2e = {"value": n_tr_tot / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(sum(p.numel() * p.element_size() for p in pins)),
                "d2h_bytes_per_step": 32,
-               "api": "g2vec_b200.CbowModel step (C ABI kernels), windows re-uploaded from pinned host memory and "
-                      "accuracies read back every step"}
+               "api": "g2vec_b200.CbowModel step (C ABI kernels); every step's windows are uploaded from pinned host "
+                      "memory (double-buffered on a copy stream) and the accuracies are read back every step"}
 
     clocks = sampler.stop() if sampler else None
     total_launches = _capi.launch_count() - launches0

@@ -83,12 +83,13 @@ class CbowModel:
         if algo not in ("rows", "rank1"):
             raise ValueError("algo must be 'rows' (gather/scatter of embedding rows) or 'rank1' (collapsed)")
         self.algo = algo
-        self.g_ho = z(self.D)
         if algo == "rows":
+            self.g_ho = z(self.D)
             self.g_ih = z(self.V, self.D)
             self.s = self.c = None
         else:                       # rank-1: s = W_ih.W_ho, c = X^T.dO; no dense gradient
             self.g_ih = None
+            self.g_ho = z(int(self.lib.g2v_cbow_r1_scratch_bytes(self.D)) // 4)   # per-block partials of W_ih^T.c
             self.s, self.c = z(self.V), z(self.V)
         if self.opt == _capi.OPT_ADAM_TF1:
             self.m_ih, self.v_ih, self.m_ho, self.v_ho = z(self.V, self.D), z(self.V, self.D), z(self.D), z(self.D)

@@ -138,11 +138,15 @@ r1_csc_reduce_kernel(const int32_t *__restrict__ cscptr, const int32_t *__restri
 template <int VEC, int OPT>
 __global__ void __launch_bounds__(kR1Warps * 32)
 r1_update_kernel(float *__restrict__ W_ih, float *__restrict__ M, float *__restrict__ Vv,
-                 const float *__restrict__ W_ho, float *__restrict__ c, float *__restrict__ g_ho, int32_t V,
+                 const float *__restrict__ W_ho, float *__restrict__ c, float *__restrict__ g_part, int32_t V,
                  int32_t D, float alpha, float omb1, float omb2, float eps) {
-    extern __shared__ float sh_gho[];              // [D]
+    // g_ho = W_ih^T . c is reduced WITHOUT atomics so that the step is bit-reproducible: every warp owns a
+    // row of sh_gho, the block sums its rows in warp order into g_part[blockIdx.x][:], and
+    // r1_update_ho_kernel sums the blocks in block order.
+    extern __shared__ float sh_gho[];              // [kR1Warps][D]
     const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) sh_gho[i] = 0.f;
+    float *my = sh_gho + (size_t)(threadIdx.x >> 5) * D;
+    for (int i = threadIdx.x; i < kR1Warps * D; i += blockDim.x) sh_gho[i] = 0.f;
     __syncthreads();
     const int64_t warp = (int64_t)blockIdx.x * kR1Warps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kR1Warps;
@@ -181,18 +185,14 @@ r1_update_kernel(float *__restrict__ W_ih, float *__restrict__ M, float *__restr
             if (lane == 0) c[g] = 0.f;
         }
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            float *p = sh_gho + (v * 32 + lane) * 4;
-            atomicAdd(p + 0, acc[v].x); atomicAdd(p + 1, acc[v].y);
-            atomicAdd(p + 2, acc[v].z); atomicAdd(p + 3, acc[v].w);
-        }
+        for (int v = 0; v < NV; ++v) reinterpret_cast<float4 *>(my)[v * 32 + lane] = acc[v];
     } else {
         for (int64_t g = warp; g < V; g += nwarps) {
             const float cg = c[g];
             float *w = W_ih + (size_t)g * D;
             for (int d = lane; d < D; d += 32) {
                 float x = w[d];
-                if (cg != 0.f) atomicAdd(sh_gho + d, cg * x);
+                if (cg != 0.f) my[d] += cg * x;            // lane-owned element of the warp's row
                 if (OPT == G2V_OPT_ADAM_TF1) {
                     float m = M[(size_t)g * D + d], vv = Vv[(size_t)g * D + d];
                     adam1_r1(x, m, vv, cg * __ldg(W_ho + d), alpha, omb1, omb2, eps);
@@ -208,19 +208,22 @@ r1_update_kernel(float *__restrict__ W_ih, float *__restrict__ M, float *__restr
     }
     __syncthreads();
     for (int i = threadIdx.x; i < D; i += blockDim.x) {
-        const float x = sh_gho[i];
-        if (x != 0.f) atomicAdd(g_ho + i, x);
+        float x = 0.f;
+#pragma unroll
+        for (int w = 0; w < kR1Warps; ++w) x += sh_gho[(size_t)w * D + i];
+        g_part[(size_t)blockIdx.x * D + i] = x;
     }
 }
 
 template <int OPT>
 __global__ void r1_update_ho_kernel(float *__restrict__ W_ho, float *__restrict__ m, float *__restrict__ v,
-                                    float *__restrict__ g_ho, int32_t D, float alpha, float omb1, float omb2,
-                                    float eps) {
+                                    const float *__restrict__ g_part, int32_t n_part, int32_t D, float alpha,
+                                    float omb1, float omb2, float eps) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < D) {
         float w = W_ho[i];
-        const float g = g_ho[i];
+        float g = 0.f;
+        for (int p = 0; p < n_part; ++p) g += g_part[(size_t)p * D + i];     // fixed order
         if (OPT == G2V_OPT_ADAM_TF1) {
             float mm = m[i], vv = v[i];
             adam1_r1(w, mm, vv, g, alpha, omb1, omb2, eps);
@@ -229,7 +232,6 @@ __global__ void r1_update_ho_kernel(float *__restrict__ W_ho, float *__restrict_
             w -= alpha * g;
         }
         W_ho[i] = w;
-        g_ho[i] = 0.f;
     }
 }
 
@@ -310,10 +312,13 @@ extern "C" int g2v_cbow_r1_windows_csc(const int32_t *rowptr, const int32_t *gen
     return 0;
 }
 
+constexpr int kR1MaxParts = 1024;   // upper bound on the update kernel's grid (scratch = kR1MaxParts * D floats)
+
 template <int VEC, int OPT>
 static int launch_r1_update(float *W_ih, float *M, float *Vv, const float *W_ho, float *c, float *g_ho, int32_t V,
-                            int32_t D, float alpha, float omb1, float omb2, float eps, cudaStream_t st) {
-    const size_t smem = (size_t)D * sizeof(float);
+                            int32_t D, float alpha, float omb1, float omb2, float eps, cudaStream_t st,
+                            int *grid_out) {
+    const size_t smem = (size_t)kR1Warps * D * sizeof(float);
     DeviceProps dp;
     if (device_props(&dp)) return 1;
     G2V_REQUIRE(smem <= (size_t)dp.max_smem_optin, "sizeHiddenlayer %d too large", D);
@@ -321,11 +326,15 @@ static int launch_r1_update(float *W_ih, float *M, float *Vv, const float *W_ho,
         G2V_CUDA_OK(cudaFuncSetAttribute(r1_update_kernel<VEC, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = 0, rc;
     if ((rc = r1_grid((const void *)r1_update_kernel<VEC, OPT>, smem, V, &grid))) return rc;
+    if (grid > kR1MaxParts) grid = kR1MaxParts;
     r1_update_kernel<VEC, OPT><<<grid, kR1Warps * 32, smem, st>>>(W_ih, M, Vv, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps);
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
+    *grid_out = grid;
     return 0;
 }
+
+extern "C" size_t g2v_cbow_r1_scratch_bytes(int32_t D) { return (size_t)kR1MaxParts * (size_t)(D > 0 ? D : 1) * sizeof(float); }
 
 extern "C" int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
                                   float *c, float *g_ho, float *s, int32_t V, int32_t D, int32_t optimizer,
@@ -342,11 +351,11 @@ extern "C" int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *
         alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
         omb1 = 1.f - beta1; omb2 = 1.f - beta2;
     }
-    int rc;
+    int rc, parts = 0;
 #define G2V_R1(VEC)                                                                                             \
     rc = optimizer == G2V_OPT_ADAM_TF1                                                                          \
-             ? launch_r1_update<VEC, G2V_OPT_ADAM_TF1>(W_ih, m_ih, v_ih, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps, st) \
-             : launch_r1_update<VEC, G2V_OPT_SGD>(W_ih, nullptr, nullptr, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps, st)
+             ? launch_r1_update<VEC, G2V_OPT_ADAM_TF1>(W_ih, m_ih, v_ih, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps, st, &parts) \
+             : launch_r1_update<VEC, G2V_OPT_SGD>(W_ih, nullptr, nullptr, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps, st, &parts)
     if (D == 128) { G2V_R1(1); }
     else if (D == 256) { G2V_R1(2); }
     else if (D == 512) { G2V_R1(4); }
@@ -354,9 +363,9 @@ extern "C" int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *
 #undef G2V_R1
     if (rc) return rc;
     if (optimizer == G2V_OPT_ADAM_TF1)
-        r1_update_ho_kernel<G2V_OPT_ADAM_TF1><<<(D + 127) / 128, 128, 0, st>>>(W_ho, m_ho, v_ho, g_ho, D, alpha, omb1, omb2, eps);
+        r1_update_ho_kernel<G2V_OPT_ADAM_TF1><<<(D + 127) / 128, 128, 0, st>>>(W_ho, m_ho, v_ho, g_ho, parts, D, alpha, omb1, omb2, eps);
     else
-        r1_update_ho_kernel<G2V_OPT_SGD><<<(D + 127) / 128, 128, 0, st>>>(W_ho, nullptr, nullptr, g_ho, D, alpha, omb1, omb2, eps);
+        r1_update_ho_kernel<G2V_OPT_SGD><<<(D + 127) / 128, 128, 0, st>>>(W_ho, nullptr, nullptr, g_ho, parts, D, alpha, omb1, omb2, eps);
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
     return g2v_cbow_r1_prepare(W_ih, W_ho, s, V, D, stream);

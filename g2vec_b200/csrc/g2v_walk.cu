@@ -256,10 +256,12 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
     if (device_props(&dp)) return 1;
     G2V_REQUIRE(dp.cc_major == 10, "g2v_walk_launch: needs an sm_100 device (found sm_%d%d)", dp.cc_major, dp.cc_minor);
 
-    // lanes per walker from the mean out-degree (a chunk of TILE neighbours per load; 4 chunks are cached)
-    const char *ft = getenv("G2V_WALK_TILE");                     // test hook: 8 / 16 / 32
-    const double mean_deg = (double)E / (double)V;
-    int tile = mean_deg <= 6.0 ? 8 : (mean_deg <= 20.0 ? 16 : 32);   // measured: profiles/README.md
+    // lanes per walker.  A full warp per walker is the fastest width on every graph measured -- syn10k
+    // (mean degree 50): 3.3 ms at 32 lanes, 4.5 ms at 16, 6.0 ms at 8; ex_* (mean degree 3.4, 62 % of the
+    // walks are singletons): 0.35 / 0.51 / 0.76 ms (profiles/README.md) -- so 8 and 16 are reachable only
+    // through the G2V_WALK_TILE hook that the tests use.
+    const char *ft = getenv("G2V_WALK_TILE");
+    int tile = 32;
     if (ft && (atoi(ft) == 8 || atoi(ft) == 16 || atoi(ft) == 32)) tile = atoi(ft);
     const int nt = 32 / tile;
     // visited set per walker: a V-bit bitmap when a CTA's bitmaps fit 56 KB (>= 4 CTAs per SM), else a hash set

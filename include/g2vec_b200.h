@@ -131,8 +131,9 @@ int g2v_cbow_step_host(const int32_t *rowptr, const int32_t *gene, const uint8_t
  *   accumulated as in g2v_cbow_fwdbwd.  c == NULL: accuracy pass only (g2v_cbow_eval).
  * g2v_cbow_r1_update: optimizer epilogue from c (after its all-reduce when multi-GPU): per row
  *   g = c[g]*W_ho and g_ho += c[g]*W_ih[g,:] (old W_ih), TF1 Adam / SGD on W_ih, then on W_ho,
- *   zeroes c and g_ho, and refreshes s for the updated parameters.  g_ho: [D] scratch, zero on
- *   entry and on exit.
+ *   zeroes c, and refreshes s for the updated parameters.  g_ho: scratch of
+ *   g2v_cbow_r1_scratch_bytes(D) bytes (per-block partial sums of W_ih^T.c, reduced in a fixed
+ *   order: no floating-point atomics anywhere in this call).
  * ------------------------------------------------------------------------------------- */
 int g2v_cbow_r1_prepare(const float *W_ih, const float *W_ho, float *s, int32_t V, int32_t D,
                         void *stream);
@@ -148,6 +149,7 @@ int g2v_cbow_r1_windows_csc(const int32_t *rowptr, const int32_t *gene, const ui
                             const int32_t *win, int64_t n_win, float inv_n_total, const float *s,
                             const int32_t *cscptr, const int32_t *csc_pos, float *dO, float *c,
                             double *loss_sum, int64_t *n_correct, int32_t V, int32_t reduce, void *stream);
+size_t g2v_cbow_r1_scratch_bytes(int32_t D);
 int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
                        float *c, float *g_ho, float *s, int32_t V, int32_t D, int32_t optimizer,
                        float lr, float beta1, float beta2, float eps, int32_t t, void *stream);
