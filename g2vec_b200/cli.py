@@ -150,8 +150,27 @@ def write_vectors(prefix, genes, mat):
 
 
 # ------------------------------------------------------------------------------------------ main
+def _distributed():
+    """One process per GPU under torchrun (RANK / WORLD_SIZE / LOCAL_RANK in the environment): NCCL group,
+    device = LOCAL_RANK.  Returns (rank, world, dist or None)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, None
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), world, dist
+
+
 def main(argv=None):
     args = parse_arguments(argv)
+    rank, world, dist = _distributed()
+    import builtins
+    print = builtins.print if rank == 0 else (lambda *a, **k: None)   # noqa: A001  every rank computes, rank 0 talks
     print('>>> 0. Arguments')
     print(args)
 
@@ -178,8 +197,22 @@ def main(argv=None):
     for i, _group in enumerate(['g', 'p']):
         rp, col, w = graph.group_csr_gpu(data['expr'], data['label'], i, src, dst)
         wg = walks.WalkGraph(rp, col, weights=w)
-        nodes, lens = walks.generate_paths(wg, args.lenPath, args.numRepetition, seed=args.seed, group=i)
-        rows.append(paths.canonical_rows(nodes, lens))
+        # walkers rank, rank+world, ...: no collective during the walk (counter-based RNG), one all_gather after
+        nodes, lens = walks.generate_paths(wg, args.lenPath, args.numRepetition, seed=args.seed, group=i,
+                                           walker_begin=rank, walker_stride=world)
+        r = paths.canonical_rows(nodes, lens)
+        if dist is not None:
+            import torch
+            cnt = torch.tensor([r.shape[0]], dtype=torch.int64, device=r.device)
+            cnts = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(cnts, cnt)
+            m = int(max(int(c[0]) for c in cnts))
+            pad = torch.full((m, r.shape[1]), paths.PAD, dtype=r.dtype, device=r.device)
+            pad[:r.shape[0]] = r
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad)
+            r = torch.unique(torch.cat([p[:int(c[0])] for p, c in zip(parts, cnts)], dim=0), dim=0)
+        rows.append(r)
     prow, plab = paths.integrate(rows[0], rows[1])
     w_rowptr, w_gene, w_label = paths.windows_csr(prow, plab)
     code = paths.gene_freq_codes(w_rowptr, w_gene, w_label, n_genes)
@@ -189,8 +222,12 @@ def main(argv=None):
 
     print(">>> 4. Compute distributed representations using modified CBOW")
     mat = cbow.train_cbow(w_rowptr, w_gene, w_label, n_genes, args.sizeHiddenlayer, args.learningRate,
-                          max_epoch=args.epoch, seed=args.seed)
+                          max_epoch=args.epoch, seed=args.seed, log=print if rank == 0 else None)
     genes = data['gene']
+    if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
     print('>>> 5. Find L-groups')
     lgroup = find_lgroups(mat, genes, geneFreq)
@@ -213,6 +250,9 @@ def main(argv=None):
     print('    %s_lgroups.txt' % args.RESULT_NAME)
     write_vectors(args.RESULT_NAME, genes, mat)
     print('    %s_vectors.txt' % args.RESULT_NAME)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -61,3 +61,30 @@ def init_weights(V, D, seed):
     rs = np.random.RandomState(seed)
     s = 1.0 / np.sqrt(D)
     return (np.clip(rs.randn(V, D), -2, 2) * s).astype(np.float32), (np.clip(rs.randn(D), -2, 2) * s).astype(np.float32)
+
+
+def write_ex_tsv(tmp_path):
+    """The ex_* inputs as the three TSV files the command line reads, rebuilt from the golden fixtures
+    (restricted expression + edge list), plus one gene and one edge that step 2 must drop."""
+    e = np.load(os.path.join(GOLDEN, "ex_expr.npz"))
+    gr = np.load(os.path.join(GOLDEN, "ex_graph.npz"))
+    genes = e["gene"]
+    samples = ["TCGA-%04d" % i for i in range(135)]
+    ef, cf, nf = (os.path.join(str(tmp_path), n) for n in ("E.txt", "C.txt", "N.txt"))
+    with open(ef, "w") as f:
+        f.write("PATIENT\t" + "\t".join(samples) + "\n")
+        for g, col in zip(genes, e["expr"].T):
+            f.write(g + "\t" + "\t".join(repr(float(x)) for x in col) + "\n")
+        f.write("NOT_IN_NETWORK\t" + "\t".join("0.5" for _ in samples) + "\n")
+    with open(cf, "w") as f:
+        f.write("PATIENT\tLABEL\n")
+        f.writelines("%s\t%d\n" % (s, l) for s, l in zip(samples, gr["label"]))
+    with open(nf, "w") as f:
+        f.write("src\tdest\n")
+        f.writelines("%s\t%s\n" % (genes[a], genes[b]) for a, b in zip(e["src"], e["dst"]))
+        # genes whose only partners are outside the expression data: in the network's gene set (so they stay
+        # in the common gene list, 7523) while the edge itself is dropped by step 2
+        seen = np.zeros(len(genes), bool); seen[e["src"]] = True; seen[e["dst"]] = True
+        f.writelines("%s\tNOT_IN_EXPRESSION\n" % g for g in genes[~seen])
+        f.write("%s\tNOT_IN_EXPRESSION\n" % genes[0])
+    return ef, cf, nf, genes

@@ -60,27 +60,8 @@ def test_gpu_adjacency_equals_reference_ex(golden_dir):
 
 def test_command_line_end_to_end(tmp_path, golden_dir, capsys):
     from g2vec_b200 import cli
-    e = np.load(os.path.join(golden_dir, "ex_expr.npz"))
-    gr = np.load(os.path.join(golden_dir, "ex_graph.npz"))
-    genes = e["gene"]
-    samples = ["TCGA-%04d" % i for i in range(135)]
-    ef, cf, nf = (str(tmp_path / n) for n in ("E.txt", "C.txt", "N.txt"))
-    with open(ef, "w") as f:
-        f.write("PATIENT\t" + "\t".join(samples) + "\n")
-        for g, col in zip(genes, e["expr"].T):
-            f.write(g + "\t" + "\t".join(repr(float(x)) for x in col) + "\n")
-        f.write("NOT_IN_NETWORK\t" + "\t".join("0.5" for _ in samples) + "\n")        # dropped by step 2
-    with open(cf, "w") as f:
-        f.write("PATIENT\tLABEL\n")
-        f.writelines("%s\t%d\n" % (s, l) for s, l in zip(samples, gr["label"]))
-    with open(nf, "w") as f:
-        f.write("src\tdest\n")
-        f.writelines("%s\t%s\n" % (genes[a], genes[b]) for a, b in zip(e["src"], e["dst"]))
-        # genes whose only network partners are outside the expression data: present in the network's gene
-        # set (so they stay in the common gene list, 7523) while the edge itself is dropped by step 2
-        seen = np.zeros(len(genes), bool); seen[e["src"]] = True; seen[e["dst"]] = True
-        f.writelines("%s\tNOT_IN_EXPRESSION\n" % g for g in genes[~seen])
-        f.write("%s\tNOT_IN_EXPRESSION\n" % genes[0])
+    from tests import helpers
+    ef, cf, nf, genes = helpers.write_ex_tsv(tmp_path)
     outs = []
     for run in range(2):
         prefix = str(tmp_path / ("res%d" % run))
