@@ -268,14 +268,13 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
     const int Lpad = (L + 31) & ~31;
     const int bm_words = (V + 31) / 32;
     const char *force = getenv("G2V_WALK_VISITED");               // test hook: "hash" / "bitmap"
-    bool bitmap = (size_t)kWalkWarps * nt * (Lpad + bm_words) * sizeof(int32_t) <= 56 * 1024;
+    int Hh = 64, hshift = 26;                                     // hash set: >= 3L slots, power of two
+    while (Hh < 3 * L) { Hh <<= 1; --hshift; }
+    const size_t per_tile = (size_t)kWalkWarps * nt * sizeof(int32_t);
+    const size_t bm_smem = per_tile * (Lpad + bm_words), hash_smem = per_tile * (Lpad + Hh);
+    bool bitmap = bm_smem <= 56 * 1024 || bm_smem <= hash_smem;   // occupancy first, then whichever is smaller
     if (force && force[0] == 'h') bitmap = false;
-    int H = 64, hshift = 26;
-    if (bitmap) {
-        H = bm_words;
-    } else {
-        while (H < 3 * L) { H <<= 1; --hshift; }
-    }
+    const int H = bitmap ? bm_words : Hh;
     const size_t smem = (size_t)kWalkWarps * nt * (Lpad + H) * sizeof(int32_t);
     G2V_REQUIRE(smem <= (size_t)dp.max_smem_optin, "g2v_walk_launch: lenPath %d needs %zu B of shared memory", L, smem);
     cudaStream_t st = (cudaStream_t)stream;

@@ -55,7 +55,9 @@ int64_t g2v_launch_count(void);
  *   rowptr [V+1], col [E] (ascending inside a row = dense row order), qw [E]: CSR of the
  *     group's directed adjacency (rows = out-edges, G2Vec.py:390) with weights quantised to
  *     integers, 1 <= qw <= 2^24  (q = rint(|PCC| * 2^16)).
- *   L: --lenPath, the maximum number of NODES of a path (G2Vec.py:331).  1 <= L <= 4096.
+ *   L: --lenPath, the maximum number of NODES of a path (G2Vec.py:331).  1 <= L <= 4096, and the
+ *     per-CTA path + visited-set buffers must fit shared memory: always true for L <= 1365, and
+ *     for any L <= 4096 while V <= ~90k (bitmap visited set); otherwise the call fails with a message.
  *   seed/group: Philox4x32-10 key and the high bits of the walker's subsequence
  *     (subsequence = group*2^40 + w, 64-bit draw s = words 2s,2s+1), so that any
  *     (walker, step) is addressable independently: results do not depend on sharding.
