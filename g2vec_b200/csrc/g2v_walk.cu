@@ -285,12 +285,9 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
                                        {walk_kernel<true, 8>, walk_kernel<true, 16>, walk_kernel<true, 32>}};
     const int ti = tile == 8 ? 0 : (tile == 16 ? 1 : 2);
     kern_t kern = table[bitmap][ti];
-    static bool attr_done[2][3] = {{false, false, false}, {false, false, false}};
-    if (!attr_done[bitmap][ti]) {
-        G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
-        G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_done[bitmap][ti] = true;
-    }
+    // per-device function attributes (set on every call: the process may have switched device)
+    G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
+    G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     G2V_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWalkWarps * 32, smem));
     G2V_REQUIRE(per_sm > 0, "g2v_walk_launch: kernel does not fit on an SM");
