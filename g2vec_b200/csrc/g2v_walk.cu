@@ -27,7 +27,6 @@
 namespace g2v {
 
 constexpr int kWalkWarps = 8;   // warps per CTA
-constexpr int kKC = 4;          // neighbour chunks (of 32) cached in registers
 
 __device__ __forceinline__ uint32_t hash_slot(int32_t c, int shift) {
     return ((uint32_t)c * 2654435761u) >> shift;
@@ -52,8 +51,10 @@ __device__ __forceinline__ bool visited(const int32_t *__restrict__ hs, uint32_t
 // machine -- every iteration is "one step for every tile of the warp" -- so that tiles whose walkers end
 // at different times stay converged: finishing a walk (row write-out, visited-set reset) and fetching
 // the next ticket are short predicated sections of the same iteration.
-template <bool BITMAP, int TILE>
-__global__ void __launch_bounds__(kWalkWarps * 32)
+// KC = neighbour chunks (of TILE) kept in registers between the two passes: 2 for graphs whose rows
+// mostly fit 64 neighbours (fewer registers -> 8 resident CTAs per SM), 4 otherwise.
+template <bool BITMAP, int TILE, int KC>
+__global__ void __launch_bounds__(kWalkWarps * 32, KC == 2 ? 8 : 6)
 walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             const uint32_t *__restrict__ qw, int32_t V, int32_t L, int32_t Lpad, int32_t H,
             int32_t hshift, uint64_t seed, uint32_t group, int64_t walker_begin,
@@ -123,11 +124,11 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             __syncwarp(tmask);
 
             // ---- pass 1: weight of the unvisited out-neighbours, per chunk of TILE (REDUX.SUM)
-            uint32_t mq[kKC], tot[kKC];
-            int32_t mc[kKC];
+            uint32_t mq[KC], tot[KC];
+            int32_t mc[KC];
             unsigned long long T = 0;
 #pragma unroll
-            for (int k = 0; k < kKC; ++k) {
+            for (int k = 0; k < KC; ++k) {
                 mq[k] = 0; mc[k] = -1; tot[k] = 0;
                 if (b + k * TILE < e) {                  // tile-uniform
                     const int32_t j = b + k * TILE + tl;
@@ -141,12 +142,13 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                     T += tot[k];
                 }
             }
-            for (int32_t jb = b + kKC * TILE; jb < e; jb += TILE) {   // rows longer than kKC*TILE neighbours
+            for (int32_t jb = b + KC * TILE; jb < e; jb += TILE) {   // rows longer than KC*TILE neighbours
                 const int32_t j = jb + tl;
                 uint32_t q = 0;
                 if (j < e) q = visited<BITMAP>(hs, hmask, hshift, __ldg(col + j)) ? 0u : __ldg(qw + j);
                 T += __reduce_add_sync(tmask, q);
             }
+            const bool has_tail = b + KC * TILE < e;
             if (T == 0) {
                 end = true;                              // every neighbour already visited
             } else {
@@ -159,13 +161,22 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                 }
                 const int src = tbase + (s % TILE);
                 const uint64_t x = ((uint64_t)__shfl_sync(tmask, dhi, src) << 32) | __shfl_sync(tmask, dlo, src);
-                unsigned long long rem = __umul64hi(x, T);   // r - (weight of the chunks already skipped)
+                // r = floor(x*T / 2^64).  Without a tail T < 2^32 (KC chunk totals of at most 2^29), so the
+                // product needs two 32x32 multiplies instead of a 64x64 high multiply.
+                unsigned long long rem;                  // r - (weight of the chunks already skipped)
+                if (!has_tail) {
+                    const uint32_t T32 = (uint32_t)T;
+                    const unsigned long long lo = (unsigned long long)(uint32_t)x * T32;
+                    rem = ((unsigned long long)(uint32_t)(x >> 32) * T32 + (lo >> 32)) >> 32;
+                } else {
+                    rem = __umul64hi(x, T);
+                }
 
                 // ---- pass 2: chunk that contains r (tile-uniform scalar search), then one scan inside it
                 int32_t nxt = -1;
                 bool found = false;
 #pragma unroll
-                for (int k = 0; k < kKC; ++k) {
+                for (int k = 0; k < KC; ++k) {
                     if (!found && b + k * TILE < e) {
                         if (rem < (unsigned long long)tot[k]) {
                             uint32_t incl = mq[k];
@@ -182,7 +193,7 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                         }
                     }
                 }
-                for (int32_t jb = b + kKC * TILE; !found && jb < e; jb += TILE) {
+                for (int32_t jb = b + KC * TILE; !found && jb < e; jb += TILE) {
                     const int32_t j = jb + tl;
                     int32_t c = -1;
                     uint32_t q = 0;
@@ -260,6 +271,7 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
     // (mean degree 50): 3.3 ms at 32 lanes, 4.5 ms at 16, 6.0 ms at 8; ex_* (mean degree 3.4, 62 % of the
     // walks are singletons): 0.35 / 0.51 / 0.76 ms (profiles/README.md) -- so 8 and 16 are reachable only
     // through the G2V_WALK_TILE hook that the tests use.
+    const double mean_deg = (double)E / (double)V;
     const char *ft = getenv("G2V_WALK_TILE");
     int tile = 32;
     if (ft && (atoi(ft) == 8 || atoi(ft) == 16 || atoi(ft) == 32)) tile = atoi(ft);
@@ -281,9 +293,15 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
     typedef void (*kern_t)(const int32_t *, const int32_t *, const uint32_t *, int32_t, int32_t, int32_t, int32_t,
                            int32_t, uint64_t, uint32_t, int64_t, int64_t, int64_t, int32_t *, int32_t *,
                            unsigned long long *);
-    static const kern_t table[2][3] = {{walk_kernel<false, 8>, walk_kernel<false, 16>, walk_kernel<false, 32>},
-                                       {walk_kernel<true, 8>, walk_kernel<true, 16>, walk_kernel<true, 32>}};
-    const int ti = tile == 8 ? 0 : (tile == 16 ? 1 : 2);
+    // chunks cached in registers: 2 when rows mostly fit 64 neighbours, 4 otherwise (G2V_WALK_KC overrides)
+    const char *fk = getenv("G2V_WALK_KC");
+    int kc = mean_deg <= 44.0 ? 2 : 4;
+    if (fk && (atoi(fk) == 2 || atoi(fk) == 4)) kc = atoi(fk);
+    if (tile != 32) kc = 4;
+    static const kern_t table[2][4] = {
+        {walk_kernel<false, 8, 4>, walk_kernel<false, 16, 4>, walk_kernel<false, 32, 4>, walk_kernel<false, 32, 2>},
+        {walk_kernel<true, 8, 4>, walk_kernel<true, 16, 4>, walk_kernel<true, 32, 4>, walk_kernel<true, 32, 2>}};
+    const int ti = tile == 8 ? 0 : (tile == 16 ? 1 : (kc == 4 ? 2 : 3));
     kern_t kern = table[bitmap][ti];
     // per-device function attributes (set on every call: the process may have switched device)
     G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));

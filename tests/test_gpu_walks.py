@@ -153,11 +153,12 @@ def test_hash_visited_set_path(g2v, monkeypatch):
     assert (got == want).all() and (gl == wl).all() and wl.max() == 80 and wl.min() == 1
 
 
-@pytest.mark.parametrize("tile", ["8", "16", "32"])
+@pytest.mark.parametrize("tile,kc", [("8", "4"), ("16", "4"), ("32", "4"), ("32", "2")])
 @pytest.mark.parametrize("vis", ["bitmap", "hash"])
-def test_every_tile_width_and_visited_set_is_bit_exact(g2v, monkeypatch, tile, vis):
-    """8/16/32 lanes per walker (chosen from the mean degree in production) x bitmap/hash visited set."""
+def test_every_tile_width_and_visited_set_is_bit_exact(g2v, monkeypatch, tile, kc, vis):
+    """Every kernel instantiation: 8/16/32 lanes per walker x 2/4 register-cached chunks x bitmap/hash."""
     monkeypatch.setenv("G2V_WALK_TILE", tile)
+    monkeypatch.setenv("G2V_WALK_KC", kc)
     monkeypatch.setenv("G2V_WALK_VISITED", vis)
     cases = [helpers.ex_graph(1) + (80, 2), helpers.random_graph(2000, 40, seed=1, dead_frac=0.2) + (33, 3)]
     V = 300
