@@ -254,8 +254,8 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
             model.update()
         else:                                 # mini-batches: every rank takes its 1/world slice of each batch
             per = -(-batch // world)
-            for lo in range(0, len(tr_loc), per):
-                nb = min(per, len(tr_loc) - lo)
+            for lo in range(0, -(-n_tr // world), per):     # same trip count on every rank (collectives inside)
+                nb = max(0, min(per, len(tr_loc) - lo))
                 nb_tot = nb if not dist else None
                 if dist:
                     t_nb = torch.tensor([nb], dtype=torch.int64, device=dev); dist.all_reduce(t_nb)
@@ -282,8 +282,8 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
         acc_tr = f32(int(acc[3])) / f32(max(n_tr, 1)) if show else None
         if hist and hist[-1][2] is None:
             hist[-1] = (hist[-1][0], hist[-1][1], float(acc_tr_prev))
-        if step > 0:
-            before_tr = acc_tr_prev
+        if hist:
+            before_tr = hist[-1][2]                             # ACC[tr] of the previous step (G2Vec.py:281)
         hist.append((step, float(acc_val), None if acc_tr is None else float(acc_tr)))
         if step % 5 == 0 and log:
             t1 = time.time()

@@ -1,6 +1,5 @@
 """CPU-only checks: the C-ABI library builds/loads and exports every symbol the header declares, it
 fails loudly without a GPU, and the host-side logic (quantisation, CSR, split, sharding, init)."""
-import ctypes
 import os
 import re
 

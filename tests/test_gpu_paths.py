@@ -1,6 +1,5 @@
 """GPU glue between the hot paths (canonicalise / dedup / cross-group removal / CSR windows /
 gene-frequency vote) against the oracle's restatement of G2Vec.py:288-322,345,351."""
-import numpy as np
 import pytest
 
 import oracle
@@ -11,7 +10,6 @@ pytestmark = pytest.mark.gpu
 
 
 def test_pipeline_equals_oracle_on_ex():
-    import torch
     import g2vec_b200 as g2v
     from g2vec_b200 import paths
     reps, L, seed = 2, 80, 0

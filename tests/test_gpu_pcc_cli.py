@@ -5,7 +5,6 @@ import os
 import numpy as np
 import pytest
 
-from oracle import legacy
 
 pytestmark = pytest.mark.gpu
 TOL_W = 2e-6          # |PCC| agreement: float32 NumPy pairwise sums (reference) vs double accumulation (GPU)
