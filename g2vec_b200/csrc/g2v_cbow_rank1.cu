@@ -75,30 +75,45 @@ r1_windows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict_
     constexpr bool BACKWARD = MODE != 0;
     __shared__ R1Acc sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & 7, slot = lane >> 3;          // 8 lanes per window, 4 windows per warp
     if (threadIdx.x == 0) { sh.loss = 0.0; sh.correct = 0ull; }
     __syncthreads();
     float loss_acc = 0.f;
     unsigned correct_acc = 0;
-    const int64_t warps_total = (int64_t)gridDim.x * kR1Warps;
-    for (int64_t i = (int64_t)blockIdx.x * kR1Warps + warp; i < n_win; i += warps_total) {
-        const int64_t n = win ? (int64_t)__ldg(win + win_begin + i) : win_begin + i;
-        const int32_t b = __ldg(rowptr + n), e = __ldg(rowptr + n + 1);
-        const float y = (float)__ldg(label + n);
+    const int64_t stride = (int64_t)gridDim.x * kR1Warps * 4;
+    for (int64_t base = ((int64_t)blockIdx.x * kR1Warps + warp) * 4; base < n_win; base += stride) {
+        const int64_t i = base + slot;
+        const bool active = i < n_win;
+        int32_t b = 0, e = 0;
+        float y = 0.f;
+        if (active) {
+            const int64_t n = win ? (int64_t)__ldg(win + win_begin + i) : win_begin + i;
+            b = __ldg(rowptr + n); e = __ldg(rowptr + n + 1);
+            y = (float)__ldg(label + n);
+        }
         float part = 0.f;
-        for (int32_t j = b + lane; j < e; j += 32) part += __ldg(s + __ldg(gene + j));
+        for (int32_t j = b + sub; j < e; j += 8) part += __ldg(s + __ldg(gene + j));
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
         const float scale = (reduce_mean && e > b) ? 1.f / (float)(e - b) : 1.f;
-        const float o = warp_sum(part) * scale;
-        if (lane == 0) {
+        const float o = part * scale;
+        float dO = 0.f;
+        if (active && sub == 0) {                        // one lane per window does the scalar math
             correct_acc += ((o > 0.f) == (y != 0.f)) ? 1u : 0u;
-            if (BACKWARD) loss_acc += fmaxf(o, 0.f) - o * y + log1pf(expf(-fabsf(o)));
+            if (BACKWARD) {
+                loss_acc += fmaxf(o, 0.f) - o * y + log1pf(expf(-fabsf(o)));
+                dO = (sigmoid_stable_r1(o) - y) * inv_n * scale;
+                if (MODE == 2) c[i] = dO;                // c is the dO array here
+            }
         }
         if (MODE == 1) {
-            const float dO = (sigmoid_stable_r1(o) - y) * inv_n * scale;
-            for (int32_t j = b + lane; j < e; j += 32) atomicAdd(c + __ldg(gene + j), dO);
-        } else if (MODE == 2) {
-            if (lane == 0) c[i] = (sigmoid_stable_r1(o) - y) * inv_n * scale;    // c is the dO array here
+            dO = __shfl_sync(0xffffffffu, dO, lane & ~7);
+            for (int32_t j = b + sub; j < e; j += 8) atomicAdd(c + __ldg(gene + j), dO);
         }
     }
+    loss_acc = warp_sum(loss_acc);
+    correct_acc = __reduce_add_sync(0xffffffffu, correct_acc);
     if (lane == 0) {
         if (BACKWARD) atomicAdd(&sh.loss, (double)loss_acc);
         atomicAdd(&sh.correct, (unsigned long long)correct_acc);
@@ -215,15 +230,26 @@ r1_update_kernel(float *__restrict__ W_ih, float *__restrict__ M, float *__restr
     }
 }
 
+// W_ho step: g_ho[i] = sum over the update kernel's blocks of g_part[p][i], in a fixed order (32 interleaved
+// slices, then the slices in order) so the result is bit-reproducible, then TF1 Adam / SGD.
 template <int OPT>
-__global__ void r1_update_ho_kernel(float *__restrict__ W_ho, float *__restrict__ m, float *__restrict__ v,
-                                    const float *__restrict__ g_part, int32_t n_part, int32_t D, float alpha,
-                                    float omb1, float omb2, float eps) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < D) {
-        float w = W_ho[i];
+__global__ void __launch_bounds__(1024)
+r1_update_ho_kernel(float *__restrict__ W_ho, float *__restrict__ m, float *__restrict__ v,
+                    const float *__restrict__ g_part, int32_t n_part, int32_t D, float alpha, float omb1,
+                    float omb2, float eps) {
+    __shared__ float sh[32][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    float a = 0.f;
+    if (i < D)
+        for (int p = slice; p < n_part; p += 32) a += g_part[(size_t)p * D + i];
+    sh[slice][lane] = a;
+    __syncthreads();
+    if (slice == 0 && i < D) {
         float g = 0.f;
-        for (int p = 0; p < n_part; ++p) g += g_part[(size_t)p * D + i];     // fixed order
+#pragma unroll
+        for (int q = 0; q < 32; ++q) g += sh[q][lane];
+        float w = W_ho[i];
         if (OPT == G2V_OPT_ADAM_TF1) {
             float mm = m[i], vv = v[i];
             adam1_r1(w, mm, vv, g, alpha, omb1, omb2, eps);
@@ -276,11 +302,11 @@ extern "C" int g2v_cbow_r1_windows(const int32_t *rowptr, const int32_t *gene, c
     int grid = 0, rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (c) {
-        if ((rc = r1_grid((const void *)r1_windows_kernel<1>, 0, n_win, &grid))) return rc;
+        if ((rc = r1_grid((const void *)r1_windows_kernel<1>, 0, (n_win + 3) / 4, &grid))) return rc;
         r1_windows_kernel<1><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, win_begin, n_win,
                                                             inv_n_total, s, c, loss_sum, nc, reduce);
     } else {
-        if ((rc = r1_grid((const void *)r1_windows_kernel<0>, 0, n_win, &grid))) return rc;
+        if ((rc = r1_grid((const void *)r1_windows_kernel<0>, 0, (n_win + 3) / 4, &grid))) return rc;
         r1_windows_kernel<0><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, win_begin, n_win, 0.f,
                                                             s, nullptr, nullptr, nc, reduce);
     }
@@ -301,7 +327,7 @@ extern "C" int g2v_cbow_r1_windows_csc(const int32_t *rowptr, const int32_t *gen
     unsigned long long *nc = reinterpret_cast<unsigned long long *>(n_correct);
     int grid = 0, rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = r1_grid((const void *)r1_windows_kernel<2>, 0, n_win, &grid))) return rc;
+    if ((rc = r1_grid((const void *)r1_windows_kernel<2>, 0, (n_win + 3) / 4, &grid))) return rc;
     r1_windows_kernel<2><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, 0, n_win, inv_n_total, s, dO,
                                                         loss_sum, nc, reduce);
     G2V_CUDA_OK(cudaGetLastError());
@@ -363,9 +389,9 @@ extern "C" int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *
 #undef G2V_R1
     if (rc) return rc;
     if (optimizer == G2V_OPT_ADAM_TF1)
-        r1_update_ho_kernel<G2V_OPT_ADAM_TF1><<<(D + 127) / 128, 128, 0, st>>>(W_ho, m_ho, v_ho, g_ho, parts, D, alpha, omb1, omb2, eps);
+        r1_update_ho_kernel<G2V_OPT_ADAM_TF1><<<(D + 31) / 32, 1024, 0, st>>>(W_ho, m_ho, v_ho, g_ho, parts, D, alpha, omb1, omb2, eps);
     else
-        r1_update_ho_kernel<G2V_OPT_SGD><<<(D + 127) / 128, 128, 0, st>>>(W_ho, nullptr, nullptr, g_ho, parts, D, alpha, omb1, omb2, eps);
+        r1_update_ho_kernel<G2V_OPT_SGD><<<(D + 31) / 32, 1024, 0, st>>>(W_ho, nullptr, nullptr, g_ho, parts, D, alpha, omb1, omb2, eps);
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
     return g2v_cbow_r1_prepare(W_ih, W_ho, s, V, D, stream);

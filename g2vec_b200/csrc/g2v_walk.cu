@@ -34,15 +34,20 @@ __device__ __forceinline__ uint32_t hash_slot(int32_t c, int shift) {
 
 // true if node c is in the warp's visited set.  BITMAP: hs is a V-bit bitmap (1 LDS);
 // otherwise an open-addressing hash set of node ids (-1 = empty).
+// Returns q if node c is NOT in the visited set, else 0.  `hs` indexes the dynamic shared array (kept as
+// an integer offset so that every access is a plain LDS/STS with a register offset).
+extern __shared__ int32_t g2v_walk_smem[];
 template <bool BITMAP>
-__device__ __forceinline__ bool visited(const int32_t *__restrict__ hs, uint32_t mask, int shift,
-                                        int32_t c) {
-    if (BITMAP) return (hs[c >> 5] >> (c & 31)) & 1;
+__device__ __forceinline__ uint32_t unvisited_weight(int hs, uint32_t mask, int shift, int32_t c, uint32_t q) {
+    if (BITMAP) {
+        const uint32_t bit = ((uint32_t)g2v_walk_smem[hs + (c >> 5)] >> (c & 31)) & 1u;
+        return q & (bit - 1u);                            // bit = 1 -> 0, bit = 0 -> q
+    }
     uint32_t i = hash_slot(c, shift);
     while (true) {
-        int32_t x = hs[i];
-        if (x == c) return true;
-        if (x < 0) return false;
+        const int32_t x = g2v_walk_smem[hs + i];
+        if (x == c) return 0u;
+        if (x < 0) return q;
         i = (i + 1) & mask;
     }
 }
@@ -60,16 +65,16 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             int32_t hshift, uint64_t seed, uint32_t group, int64_t walker_begin,
             int64_t n_walkers, int64_t walker_stride, int32_t *__restrict__ out_nodes,
             int32_t *__restrict__ out_len, unsigned long long *__restrict__ ticket) {
-    extern __shared__ int32_t smem[];
+    int32_t *const smem = g2v_walk_smem;
     constexpr int NT = 32 / TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = lane / TILE, tl = lane % TILE, tbase = tile * TILE;
     const unsigned tmask = TILE == 32 ? 0xffffffffu : (((1u << TILE) - 1u) << tbase);
-    int32_t *path = smem + (size_t)(warp * NT + tile) * (Lpad + H);
-    int32_t *hs = path + Lpad;
+    const int path = (warp * NT + tile) * (Lpad + H);   // offsets into smem (ints), not pointers
+    const int hs = path + Lpad;
     const uint32_t hmask = (uint32_t)H - 1u;
 
-    for (int i = tl; i < H; i += TILE) hs[i] = BITMAP ? 0 : -1;
+    for (int i = tl; i < H; i += TILE) smem[hs + i] = BITMAP ? 0 : -1;
     __syncwarp(tmask);
 
     bool have = false, done = false, dirty = false;
@@ -101,7 +106,7 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
         }
 
         // ---------------------------------------------------------------- one step of this tile's walker
-        path[n] = cur;                                   // every lane of the tile stores the same value
+        smem[path + n] = cur;                            // every lane of the tile stores the same value
         ++n;
         bool end = (s == L - 1);                         // the L-th node is appended, never expanded
         int32_t b = 0, e = 0;
@@ -111,14 +116,14 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
         }
         if (!end) {
             if (BITMAP) {                                // visited.insert(cur), uniform across the tile
-                const int32_t wv = hs[cur >> 5];
+                const int32_t wv = smem[hs + (cur >> 5)];
                 __syncwarp(tmask);
-                hs[cur >> 5] = wv | (1 << (cur & 31));
+                smem[hs + (cur >> 5)] = wv | (1 << (cur & 31));
             } else {
                 uint32_t i = hash_slot(cur, hshift);
-                while (hs[i] >= 0) i = (i + 1) & hmask;
+                while (smem[hs + i] >= 0) i = (i + 1) & hmask;
                 __syncwarp(tmask);
-                hs[i] = cur;
+                smem[hs + i] = cur;
             }
             dirty = true;
             __syncwarp(tmask);
@@ -130,14 +135,13 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 mq[k] = 0; mc[k] = -1; tot[k] = 0;
-                if (b + k * TILE < e) {                  // tile-uniform
+                if (k == 0 || b + k * TILE < e) {        // tile-uniform (chunk 0 always exists: b < e)
                     const int32_t j = b + k * TILE + tl;
-                    if (j < e) {
-                        const int32_t c = __ldg(col + j);
-                        const uint32_t q = __ldg(qw + j);
-                        mc[k] = c;
-                        mq[k] = visited<BITMAP>(hs, hmask, hshift, c) ? 0u : q;
-                    }
+                    const bool in = j < e;
+                    const int32_t c = in ? __ldg(col + j) : 0;       // predicated loads, no branch
+                    const uint32_t q = in ? __ldg(qw + j) : 0u;
+                    mc[k] = c;
+                    mq[k] = unvisited_weight<BITMAP>(hs, hmask, hshift, c, q);
                     tot[k] = __reduce_add_sync(tmask, mq[k]);         // <= 32 * 2^24
                     T += tot[k];
                 }
@@ -145,7 +149,7 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             for (int32_t jb = b + KC * TILE; jb < e; jb += TILE) {   // rows longer than KC*TILE neighbours
                 const int32_t j = jb + tl;
                 uint32_t q = 0;
-                if (j < e) q = visited<BITMAP>(hs, hmask, hshift, __ldg(col + j)) ? 0u : __ldg(qw + j);
+                if (j < e) q = unvisited_weight<BITMAP>(hs, hmask, hshift, __ldg(col + j), __ldg(qw + j));
                 T += __reduce_add_sync(tmask, q);
             }
             const bool has_tail = b + KC * TILE < e;
@@ -177,7 +181,7 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                 bool found = false;
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
-                    if (!found && b + k * TILE < e) {
+                    if (!found && (k == 0 || b + k * TILE < e)) {
                         if (rem < (unsigned long long)tot[k]) {
                             uint32_t incl = mq[k];
 #pragma unroll
@@ -199,7 +203,7 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                     uint32_t q = 0;
                     if (j < e) {
                         c = __ldg(col + j);
-                        q = visited<BITMAP>(hs, hmask, hshift, c) ? 0u : __ldg(qw + j);
+                        q = unvisited_weight<BITMAP>(hs, hmask, hshift, c, __ldg(qw + j));
                     }
                     const uint32_t ct = __reduce_add_sync(tmask, q);
                     if (rem < (unsigned long long)ct) {
@@ -223,14 +227,14 @@ walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
         if (end) {                                       // walk finished: write the row once, coalesced
             __syncwarp(tmask);
             int32_t *row = out_nodes + (size_t)t * (size_t)L;
-            for (int i = tl; i < L; i += TILE) row[i] = (i < n) ? path[i] : -1;
+            for (int i = tl; i < L; i += TILE) row[i] = (i < n) ? smem[path + i] : -1;
             if (tl == 0) out_len[t] = n;
             if (dirty) {
                 __syncwarp(tmask);
                 if (BITMAP) {
-                    for (int i = tl; i < n; i += TILE) hs[path[i] >> 5] = 0;   // only the words this walk touched
+                    for (int i = tl; i < n; i += TILE) smem[hs + (smem[path + i] >> 5)] = 0;   // only the touched words
                 } else {
-                    for (int i = tl; i < H; i += TILE) hs[i] = -1;
+                    for (int i = tl; i < H; i += TILE) smem[hs + i] = -1;
                 }
             }
             __syncwarp(tmask);
