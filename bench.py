@@ -288,6 +288,17 @@ def run_b200(args):
              "upd_ms": allmax(float(np.mean([m[1] for m in marks]))),
              "val_ms": allmax(float(np.mean([m[2] for m in marks]))),
              "acc_val": int(acc_pin[2]) / max(n_va_tot, 1), "model": model, "step": step}
+        r["eager_ms"] = r["step_ms"]
+        if world == 1:
+            # what g2vec_b200.train_cbow runs on one GPU: the same launches replayed as one CUDA graph
+            gstep = model.make_step(tr_d, n_tr_tot, va_d, acc_pin, True)
+            timed(gstep, W)
+            barrier()
+            gt, _ = timed(gstep, K)
+            barrier()
+            r["step_ms"] = float(np.mean(gt))
+            r["launches"] += 0                 # replays launch the same kernels; counted once below
+            r["graph"] = True
         r["value"] = n_tr_tot / (r["step_ms"] * 1e-3)
         return r
 
@@ -388,12 +399,14 @@ def run_b200(args):
                            " (10 per GPU)" if args.scaling == "weak" and world > 1 else ""),
                        "windows_train": n_tr_tot, "windows_val": n_va_tot, "mean_window_len": float(lens_np.mean()),
                        "optimizer": args.optimizer, "step": "fwd+bwd+update + val acc + train acc (G2Vec.py:262-267)",
+                       "launch": ("one CUDA graph replay per step (eager launches: %.3f ms per step)" % main["eager_ms"])
+                                 if main.get("graph") else "eager launches",
                        "parallelism": "dp%d (windows/walkers sharded, W replicated, dense grad all-reduce per step)" % world,
                        "l2": "256 MiB flush write before every timed step"},
             "train_only": {"value": n_tr_tot / (upd_ms * 1e-3), "unit": UNIT, "ms_per_step": upd_ms,
                            "note": "fwd+bwd+all-reduce+update, without the two accuracy passes"},
             "production_loop": {
-                "value": n_tr_tot / ((main["val_ms"] + (step_ms - main["val_ms"]) / 5.0) * 1e-3), "unit": UNIT,
+                "value": n_tr_tot / ((step_ms - 0.8 * (main["eager_ms"] - main["val_ms"])) * 1e-3), "unit": UNIT,
                 "note": "what g2vec_b200.train_cbow runs: the training-accuracy pass of G2Vec.py:267 equals the next "
                         "step's training forward, so the separate pass is executed only on the steps that print it "
                         "(every 5th); derived from the same timed steps as `value`"},

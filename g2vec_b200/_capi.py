@@ -26,7 +26,8 @@ SIGNATURES = {
     "g2v_cbow_fwdbwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _i32, _i32, _i32, _vp]),
     "g2v_cbow_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32,
-                                       _f32, _f32, _i32, _vp]),
+                                       _f32, _f32, _i32, _vp, _vp]),
+    "g2v_cbow_adam_tick": (ctypes.c_int, [_vp, _f32, _f32, _f32, _vp]),
     "g2v_cbow_eval": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "g2v_cbow_step_host": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                           _i32, _i32, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
@@ -36,7 +37,7 @@ SIGNATURES = {
                                               _i32, _i32, _vp]),
     "g2v_cbow_r1_scratch_bytes": (ctypes.c_size_t, [_i32]),
     "g2v_cbow_r1_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32,
-                                         _f32, _f32, _i32, _vp]),
+                                         _f32, _f32, _i32, _vp, _vp]),
     "g2v_pcc_zscore": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "g2v_pcc_edge_weights": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
     "g2v_test_draws": (ctypes.c_int, [_u64, _u64, _i32, _vp, _vp]),

@@ -98,6 +98,9 @@ class CbowModel:
         # [loss_sum (f64 bits), n_correct_train_fwd, n_correct_val, n_correct_train] as 4 x 8 bytes
         self.acc = torch.zeros(4, dtype=torch.int64, device=dev)
         self.t = 0
+        # Adam's beta1^t / beta2^t / alpha_t live on the device (TF1's beta*_power variables), advanced by
+        # g2v_cbow_adam_tick: no launch of a step depends on a host-side value, so a step can be a CUDA graph
+        self.hyper = torch.tensor([1.0, 1.0, 0.0, 0.0], dtype=torch.float32, device=dev)
         if algo == "rank1":
             _capi.check(self.lib.g2v_cbow_r1_prepare(self.W_ih.data_ptr(), self.W_ho.data_ptr(), self.s.data_ptr(),
                                                      self.V, self.D, self._stream()), "g2v_cbow_r1_prepare")
@@ -163,18 +166,23 @@ class CbowModel:
 
     def update(self):
         self.t += 1
+        adev = 0
+        if self.opt == _capi.OPT_ADAM_TF1:
+            _capi.check(self.lib.g2v_cbow_adam_tick(self.hyper.data_ptr(), self.lr, self.beta1, self.beta2,
+                                                    self._stream()), "g2v_cbow_adam_tick")
+            adev = self.hyper.data_ptr()
         if self.algo == "rank1":
             rc = self.lib.g2v_cbow_r1_update(self.W_ih.data_ptr(), self.W_ho.data_ptr(), self._ptr(self.m_ih),
                                              self._ptr(self.v_ih), self._ptr(self.m_ho), self._ptr(self.v_ho),
                                              self.c.data_ptr(), self.g_ho.data_ptr(), self.s.data_ptr(), self.V,
                                              self.D, self.opt, self.lr, self.beta1, self.beta2, self.eps, self.t,
-                                             self._stream())
+                                             adev, self._stream())
             _capi.check(rc, "g2v_cbow_r1_update")
             return
         rc = self.lib.g2v_cbow_update(self.W_ih.data_ptr(), self.W_ho.data_ptr(), self._ptr(self.m_ih),
                                       self._ptr(self.v_ih), self._ptr(self.m_ho), self._ptr(self.v_ho),
                                       self.g_ih.data_ptr(), self.g_ho.data_ptr(), self.V, self.D, self.opt,
-                                      self.lr, self.beta1, self.beta2, self.eps, self.t, self._stream())
+                                      self.lr, self.beta1, self.beta2, self.eps, self.t, adev, self._stream())
         _capi.check(rc, "g2v_cbow_update")
 
     def evaluate(self, win, slot, win_begin=0, n_win=None):
@@ -192,6 +200,33 @@ class CbowModel:
                                     self.reduce, self._stream())
         _capi.check(rc, "g2v_cbow_eval")
 
+    def make_step(self, tr_d, n_tr, va_d, acc_pin, with_train_eval, use_graph=True):
+        """One iteration of the reference loop (G2Vec.py:262-267) on ONE GPU as a replayable callable:
+        zero counters, fwd+bwd, optimizer, validation accuracy, optionally training accuracy, counters ->
+        pinned host memory.  With use_graph the launches are captured once into a CUDA graph."""
+        def body():
+            self.acc.zero_()
+            if tr_d.shape[0]:
+                self.fwdbwd(tr_d, n_tr)
+            self.update()
+            if va_d.shape[0]:
+                self.evaluate(va_d, 2)
+            if with_train_eval and tr_d.shape[0]:
+                self.evaluate(tr_d, 3)
+            acc_pin.copy_(self.acc, non_blocking=True)
+        if not use_graph:
+            return body
+        g = torch.cuda.CUDAGraph()
+        t_before = self.t
+        with torch.cuda.graph(g):
+            body()
+        self.t = t_before                    # capture records, it does not execute
+
+        def replay():
+            self.t += 1
+            g.replay()
+        return replay
+
     def loss_sum(self, acc_host):
         return float(acc_host[:1].view(torch.float64)[0])
 
@@ -205,7 +240,7 @@ def _dist():
 
 def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500, seed=0, optimizer="adam",
                reduce="sum", W_ih0=None, W_ho0=None, split=None, early_stop=True, log=print, return_info=False,
-               eval_train="lazy", algo="rows", batch=0):
+               eval_train="lazy", algo="rows", batch=0, use_graph=True):
     """Train the modified CBOW on CSR windows and return W_ih (np.float32 [n_genes, hidden]) exactly as
     ``compute_genetovec`` does: the weights after the last step whose validation accuracy did not drop.
 
@@ -216,6 +251,10 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
     reference does (:262-264).  ``batch = B > 0`` is the north_star's mini-batch variant: the (already
     shuffled) training windows are cut into consecutive batches of B, one optimizer step (and, multi-GPU,
     one gradient all-reduce) per batch, loss mean over the batch; ``batch >= n_train`` equals full batch.
+
+    ``use_graph``: on one GPU with full batch, every step after the first replays a CUDA graph of the step's
+    launches (the Adam step size lives on the device, g2v_cbow_adam_tick), so the host only replays, waits
+    and applies the early-stop rule.
     """
     dist = _dist()
     world, rank = (dist.get_world_size(), dist.get_rank()) if dist else (1, 0)
@@ -243,20 +282,25 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
     result = model.W_ih.clone()
     hist, stop = [], None
     f32 = np.float32
-    for step in range(max_epoch):
+    full_batch = batch <= 0 or batch >= n_tr
+    graph_ok = use_graph and dist is None and full_batch
+    acc_pin = torch.zeros(4, dtype=torch.int64).pin_memory()
+    steps = {}                               # with_train_eval -> CUDA-graph step (captured at first use)
+
+    def eager_step(show):
         model.acc.zero_()
-        if batch <= 0 or batch >= n_tr:
+        if full_batch:
             if len(tr_loc):
-                model.fwdbwd(tr_d, n_tr)      # acc[1] += correct predictions with the PRE-update weights
+                model.fwdbwd(tr_d, n_tr)     # acc[1] += correct predictions with the PRE-update weights
             if dist:
                 for g in model.grad_tensors():
                     dist.all_reduce(g)
             model.update()
-        else:                                 # mini-batches: every rank takes its 1/world slice of each batch
+        else:                                # mini-batches: every rank takes its 1/world slice of each batch
             per = -(-batch // world)
             for lo in range(0, -(-n_tr // world), per):     # same trip count on every rank (collectives inside)
                 nb = max(0, min(per, len(tr_loc) - lo))
-                nb_tot = nb if not dist else None
+                nb_tot = nb
                 if dist:
                     t_nb = torch.tensor([nb], dtype=torch.int64, device=dev); dist.all_reduce(t_nb)
                     nb_tot = int(t_nb[0])
@@ -267,16 +311,26 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
                 model.update()
         if len(va_loc):
             model.evaluate(va_d, 2)
-        # ACC[tr] of G2Vec.py:267 uses the post-update weights, i.e. exactly what the NEXT step's training
-        # forward computes (SURVEY 3.2-5).  It is only printed every 5th step and at the stop, so the extra
-        # forward pass is run only when its value is shown now; otherwise it arrives one step later for free.
-        show = ((step % 5 == 0 and log is not None) or step == max_epoch - 1 or eval_train == "always"
-                or 0 < batch < n_tr)          # with mini-batches acc[1] mixes weights: always evaluate
         if show and len(tr_loc):
             model.evaluate(tr_d, 3)
         if dist:
             dist.all_reduce(model.acc[1:4])
-        acc = model.acc.cpu()                                   # the step's only host sync
+        return model.acc.cpu()               # the step's only host sync
+
+    for step in range(max_epoch):
+        # ACC[tr] of G2Vec.py:267 uses the post-update weights, i.e. exactly what the NEXT step's training
+        # forward computes (SURVEY 3.2-5).  It is only printed every 5th step and at the stop, so the extra
+        # forward pass is run only when its value is shown now; otherwise it arrives one step later for free.
+        show = ((step % 5 == 0 and log is not None) or step == max_epoch - 1 or eval_train == "always"
+                or not full_batch)           # with mini-batches acc[1] mixes weights: always evaluate
+        if graph_ok and step > 0:            # step 0 runs eagerly (and warms every kernel up before capture)
+            if show not in steps:
+                steps[show] = model.make_step(tr_d, n_tr, va_d, acc_pin, show)
+            steps[show]()
+            torch.cuda.current_stream().synchronize()            # the step's only host sync
+            acc = acc_pin.clone()
+        else:
+            acc = eager_step(show)
         acc_val = f32(int(acc[2])) / f32(max(n_va, 1))
         acc_tr_prev = f32(int(acc[1])) / f32(max(n_tr, 1))      # = ACC[tr] of step-1
         acc_tr = f32(int(acc[3])) / f32(max(n_tr, 1)) if show else None

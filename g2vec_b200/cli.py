@@ -29,6 +29,9 @@ def parse_arguments(argv=None):
     p.add_argument('-l', '--learningRate', type=float, default=0.005, help='')
     p.add_argument('-n', '--numBiomarker', type=int, default=50, help='')
     p.add_argument('--seed', type=int, default=0, help='seed of the walk sampler, the split and the init')
+    p.add_argument('--algo', choices=['rows', 'rank1'], default='rows',
+                   help="CBOW kernels: 'rows' = embedding-row gather/scatter (default), 'rank1' = collapsed, "
+                        "bit-reproducible trainer; same results to fp32 rounding")
     return p.parse_args(argv)
 
 
@@ -222,7 +225,7 @@ def main(argv=None):
 
     print(">>> 4. Compute distributed representations using modified CBOW")
     mat = cbow.train_cbow(w_rowptr, w_gene, w_label, n_genes, args.sizeHiddenlayer, args.learningRate,
-                          max_epoch=args.epoch, seed=args.seed, log=print if rank == 0 else None)
+                          max_epoch=args.epoch, seed=args.seed, log=print if rank == 0 else None, algo=args.algo)
     genes = data['gene']
     if rank != 0:
         dist.barrier()

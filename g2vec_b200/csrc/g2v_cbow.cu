@@ -325,8 +325,10 @@ template <int OPT>
 __global__ void __launch_bounds__(256)
 cbow_update_kernel(float *__restrict__ W, float *__restrict__ M, float *__restrict__ Vv,
                    float *__restrict__ G, int64_t n, float *__restrict__ W2, float *__restrict__ M2,
-                   float *__restrict__ V2, float *__restrict__ G2, int64_t n2, float alpha, float omb1,
-                   float omb2, float eps) {
+                   float *__restrict__ V2, float *__restrict__ G2, int64_t n2, float alpha_host, float omb1,
+                   float omb2, float eps, const float *__restrict__ alpha_dev) {
+    // alpha_dev != NULL: the step size lives on the device (g2v_cbow_adam_tick), so the launch can be replayed
+    const float alpha = alpha_dev ? __ldg(alpha_dev + 2) : alpha_host;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t n4 = n >> 2;
@@ -444,10 +446,26 @@ extern "C" int g2v_cbow_eval(const int32_t *rowptr, const int32_t *gene, const u
                               nullptr, n_correct, D, reduce, (cudaStream_t)stream);
 }
 
+__global__ void adam_tick_kernel(float *state, float lr, float beta1, float beta2) {
+    // TF1's beta1_power / beta2_power variables, advanced once per optimizer step on the device
+    const float b1p = state[0] * beta1, b2p = state[1] * beta2;
+    state[0] = b1p; state[1] = b2p;
+    state[2] = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+}
+
+extern "C" int g2v_cbow_adam_tick(float *state, float lr, float beta1, float beta2, void *stream) {
+    G2V_REQUIRE(state != nullptr, "g2v_cbow_adam_tick: null pointer");
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2);
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 extern "C" int g2v_cbow_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
                                float *g_ih, float *g_ho, int32_t V, int32_t D, int32_t optimizer, float lr,
-                               float beta1, float beta2, float eps, int32_t t, void *stream) {
-    G2V_REQUIRE(V > 0 && D > 0 && t >= 1, "g2v_cbow_update: bad sizes (V=%d D=%d t=%d)", V, D, t);
+                               float beta1, float beta2, float eps, int32_t t, const float *alpha_dev,
+                               void *stream) {
+    G2V_REQUIRE(V > 0 && D > 0 && (t >= 1 || alpha_dev), "g2v_cbow_update: bad sizes (V=%d D=%d t=%d)", V, D, t);
     G2V_REQUIRE(W_ih && W_ho && g_ih && g_ho, "g2v_cbow_update: null pointer");
     G2V_REQUIRE(optimizer == G2V_OPT_ADAM_TF1 || optimizer == G2V_OPT_SGD, "g2v_cbow_update: unknown optimizer %d", optimizer);
     G2V_REQUIRE(optimizer == G2V_OPT_SGD || (m_ih && v_ih && m_ho && v_ho), "g2v_cbow_update: Adam needs m/v buffers");
@@ -463,12 +481,13 @@ extern "C" int g2v_cbow_update(float *W_ih, float *W_ho, float *m_ih, float *v_i
         // beta^t by repeated float32 multiplication, as TF1's beta1_power / beta2_power variables
         float b1p = 1.f, b2p = 1.f;
         for (int i = 0; i < t; ++i) { b1p *= beta1; b2p *= beta2; }
-        const float alpha = lr * sqrtf(1.f - b2p) / (1.f - b1p);
+        const float alpha = alpha_dev ? 0.f : lr * sqrtf(1.f - b2p) / (1.f - b1p);
         cbow_update_kernel<G2V_OPT_ADAM_TF1><<<(unsigned)blocks, 256, 0, st>>>(
-            W_ih, m_ih, v_ih, g_ih, n, W_ho, m_ho, v_ho, g_ho, (int64_t)D, alpha, 1.f - beta1, 1.f - beta2, eps);
+            W_ih, m_ih, v_ih, g_ih, n, W_ho, m_ho, v_ho, g_ho, (int64_t)D, alpha, 1.f - beta1, 1.f - beta2, eps,
+            alpha_dev);
     } else {
         cbow_update_kernel<G2V_OPT_SGD><<<(unsigned)blocks, 256, 0, st>>>(
-            W_ih, nullptr, nullptr, g_ih, n, W_ho, nullptr, nullptr, g_ho, (int64_t)D, lr, 0.f, 0.f, 0.f);
+            W_ih, nullptr, nullptr, g_ih, n, W_ho, nullptr, nullptr, g_ho, (int64_t)D, lr, 0.f, 0.f, 0.f, nullptr);
     }
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
@@ -510,7 +529,7 @@ extern "C" int g2v_cbow_step_host(const int32_t *rowptr, const int32_t *gene, co
         if (rc) break;
         rc = g2v_cbow_update((float *)(d + o_W), (float *)(d + o_Wo), (float *)(d + o_m), (float *)(d + o_v),
                              (float *)(d + o_mo), (float *)(d + o_vo), (float *)(d + o_g), (float *)(d + o_go), V, D,
-                             optimizer, lr, beta1, beta2, eps, t, st);
+                             optimizer, lr, beta1, beta2, eps, t, nullptr, st);
         if (rc) break;
         rc = 1;
         D2H(W_ih, o_W, nW); D2H(W_ho, o_Wo, nD);

@@ -154,7 +154,9 @@ template <int VEC, int OPT>
 __global__ void __launch_bounds__(kR1Warps * 32)
 r1_update_kernel(float *__restrict__ W_ih, float *__restrict__ M, float *__restrict__ Vv,
                  const float *__restrict__ W_ho, float *__restrict__ c, float *__restrict__ g_part, int32_t V,
-                 int32_t D, float alpha, float omb1, float omb2, float eps) {
+                 int32_t D, float alpha_host, float omb1, float omb2, float eps,
+                 const float *__restrict__ alpha_dev) {
+    const float alpha = alpha_dev ? __ldg(alpha_dev + 2) : alpha_host;
     // g_ho = W_ih^T . c is reduced WITHOUT atomics so that the step is bit-reproducible: every warp owns a
     // row of sh_gho, the block sums its rows in warp order into g_part[blockIdx.x][:], and
     // r1_update_ho_kernel sums the blocks in block order.
@@ -235,8 +237,9 @@ r1_update_kernel(float *__restrict__ W_ih, float *__restrict__ M, float *__restr
 template <int OPT>
 __global__ void __launch_bounds__(1024)
 r1_update_ho_kernel(float *__restrict__ W_ho, float *__restrict__ m, float *__restrict__ v,
-                    const float *__restrict__ g_part, int32_t n_part, int32_t D, float alpha, float omb1,
-                    float omb2, float eps) {
+                    const float *__restrict__ g_part, int32_t n_part, int32_t D, float alpha_host, float omb1,
+                    float omb2, float eps, const float *__restrict__ alpha_dev) {
+    const float alpha = alpha_dev ? __ldg(alpha_dev + 2) : alpha_host;
     __shared__ float sh[32][33];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + lane;
@@ -342,8 +345,8 @@ constexpr int kR1MaxParts = 1024;   // upper bound on the update kernel's grid (
 
 template <int VEC, int OPT>
 static int launch_r1_update(float *W_ih, float *M, float *Vv, const float *W_ho, float *c, float *g_ho, int32_t V,
-                            int32_t D, float alpha, float omb1, float omb2, float eps, cudaStream_t st,
-                            int *grid_out) {
+                            int32_t D, float alpha, float omb1, float omb2, float eps, const float *alpha_dev,
+                            cudaStream_t st, int *grid_out) {
     const size_t smem = (size_t)kR1Warps * D * sizeof(float);
     DeviceProps dp;
     if (device_props(&dp)) return 1;
@@ -353,7 +356,8 @@ static int launch_r1_update(float *W_ih, float *M, float *Vv, const float *W_ho,
     int grid = 0, rc;
     if ((rc = r1_grid((const void *)r1_update_kernel<VEC, OPT>, smem, V, &grid))) return rc;
     if (grid > kR1MaxParts) grid = kR1MaxParts;
-    r1_update_kernel<VEC, OPT><<<grid, kR1Warps * 32, smem, st>>>(W_ih, M, Vv, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps);
+    r1_update_kernel<VEC, OPT><<<grid, kR1Warps * 32, smem, st>>>(W_ih, M, Vv, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps,
+                                                                  alpha_dev);
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
     *grid_out = grid;
@@ -364,8 +368,10 @@ extern "C" size_t g2v_cbow_r1_scratch_bytes(int32_t D) { return (size_t)kR1MaxPa
 
 extern "C" int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
                                   float *c, float *g_ho, float *s, int32_t V, int32_t D, int32_t optimizer,
-                                  float lr, float beta1, float beta2, float eps, int32_t t, void *stream) {
-    G2V_REQUIRE(V > 0 && D > 0 && t >= 1, "g2v_cbow_r1_update: bad sizes (V=%d D=%d t=%d)", V, D, t);
+                                  float lr, float beta1, float beta2, float eps, int32_t t, const float *alpha_dev,
+                                  void *stream) {
+    G2V_REQUIRE(V > 0 && D > 0 && (t >= 1 || alpha_dev), "g2v_cbow_r1_update: bad sizes (V=%d D=%d t=%d)", V, D, t);
+    if (optimizer != G2V_OPT_ADAM_TF1) alpha_dev = nullptr;
     G2V_REQUIRE(W_ih && W_ho && c && g_ho && s, "g2v_cbow_r1_update: null pointer");
     G2V_REQUIRE(optimizer == G2V_OPT_ADAM_TF1 || optimizer == G2V_OPT_SGD, "g2v_cbow_r1_update: unknown optimizer %d", optimizer);
     G2V_REQUIRE(optimizer == G2V_OPT_SGD || (m_ih && v_ih && m_ho && v_ho), "g2v_cbow_r1_update: Adam needs m/v buffers");
@@ -380,8 +386,8 @@ extern "C" int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *
     int rc, parts = 0;
 #define G2V_R1(VEC)                                                                                             \
     rc = optimizer == G2V_OPT_ADAM_TF1                                                                          \
-             ? launch_r1_update<VEC, G2V_OPT_ADAM_TF1>(W_ih, m_ih, v_ih, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps, st, &parts) \
-             : launch_r1_update<VEC, G2V_OPT_SGD>(W_ih, nullptr, nullptr, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps, st, &parts)
+             ? launch_r1_update<VEC, G2V_OPT_ADAM_TF1>(W_ih, m_ih, v_ih, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps, alpha_dev, st, &parts) \
+             : launch_r1_update<VEC, G2V_OPT_SGD>(W_ih, nullptr, nullptr, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps, alpha_dev, st, &parts)
     if (D == 128) { G2V_R1(1); }
     else if (D == 256) { G2V_R1(2); }
     else if (D == 512) { G2V_R1(4); }
@@ -389,9 +395,9 @@ extern "C" int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *
 #undef G2V_R1
     if (rc) return rc;
     if (optimizer == G2V_OPT_ADAM_TF1)
-        r1_update_ho_kernel<G2V_OPT_ADAM_TF1><<<(D + 31) / 32, 1024, 0, st>>>(W_ho, m_ho, v_ho, g_ho, parts, D, alpha, omb1, omb2, eps);
+        r1_update_ho_kernel<G2V_OPT_ADAM_TF1><<<(D + 31) / 32, 1024, 0, st>>>(W_ho, m_ho, v_ho, g_ho, parts, D, alpha, omb1, omb2, eps, alpha_dev);
     else
-        r1_update_ho_kernel<G2V_OPT_SGD><<<(D + 31) / 32, 1024, 0, st>>>(W_ho, nullptr, nullptr, g_ho, parts, D, alpha, omb1, omb2, eps);
+        r1_update_ho_kernel<G2V_OPT_SGD><<<(D + 31) / 32, 1024, 0, st>>>(W_ho, nullptr, nullptr, g_ho, parts, D, alpha, omb1, omb2, eps, nullptr);
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
     return g2v_cbow_r1_prepare(W_ih, W_ho, s, V, D, stream);

@@ -104,7 +104,15 @@ int g2v_cbow_fwdbwd(const int32_t *rowptr, const int32_t *gene, const uint8_t *l
 
 int g2v_cbow_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
                     float *g_ih, float *g_ho, int32_t V, int32_t D, int32_t optimizer, float lr,
-                    float beta1, float beta2, float eps, int32_t t, void *stream);
+                    float beta1, float beta2, float eps, int32_t t, const float *alpha_dev, void *stream);
+
+/* Device-resident Adam step state -- TF1 keeps beta1^t / beta2^t as variables (AdamOptimizer's
+ * beta1_power / beta2_power, G2Vec.py:246).  state = {beta1^t, beta2^t, alpha_t, unused}, initialised to
+ * {1, 1, 0, 0}; g2v_cbow_adam_tick advances it by one step on the device.  Passing the same pointer as
+ * `alpha_dev` to g2v_cbow_update / g2v_cbow_r1_update (else NULL: alpha is computed on the host from t)
+ * makes every launch of a training step independent of host-side values, so the whole step can be captured
+ * once in a CUDA graph and replayed (g2vec_b200/cbow.py). */
+int g2v_cbow_adam_tick(float *state, float lr, float beta1, float beta2, void *stream);
 
 int g2v_cbow_eval(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
                   const int32_t *win, int64_t win_begin, int64_t n_win, const float *W_ih,
@@ -154,7 +162,8 @@ int g2v_cbow_r1_windows_csc(const int32_t *rowptr, const int32_t *gene, const ui
 size_t g2v_cbow_r1_scratch_bytes(int32_t D);
 int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m_ho, float *v_ho,
                        float *c, float *g_ho, float *s, int32_t V, int32_t D, int32_t optimizer,
-                       float lr, float beta1, float beta2, float eps, int32_t t, void *stream);
+                       float lr, float beta1, float beta2, float eps, int32_t t, const float *alpha_dev,
+                       void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Upstream of the walks -- edge weighting.  Replaces construct_adjMat /

@@ -326,3 +326,27 @@ def test_rank1_csc_backward_is_bit_reproducible(g2v):
     m.prepare_csc(win); m.fwdbwd(win, N); torch.cuda.synchronize()
     c_csc = m.c.cpu().numpy()
     assert np.abs(c_csc - c_atomic).max() <= 1e-5 * np.abs(c_atomic).max()
+
+
+@pytest.mark.parametrize("algo", ["rows", "rank1"])
+def test_graph_replayed_steps_equal_eager_steps(g2v, algo):
+    """On one GPU train_cbow replays a CUDA graph per step (device-side Adam tick); results must equal the
+    eager launches: bit-identical for rank1 (no atomics), to reassociation for rows."""
+    (rowptr, gene, label), _ = helpers.ex_windows(reps=2)
+    V, D = 7523, 128
+    W0, Wo0 = helpers.init_weights(V, D, 0)
+    kw = dict(max_epoch=12, seed=0, W_ih0=W0, W_ho0=Wo0, early_stop=False, log=None, algo=algo, return_info=True)
+    a, ia = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, use_graph=True, **kw)
+    b, ib = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, use_graph=False, **kw)
+    if algo == "rank1":
+        assert (a == b).all() and ia["history"] == ib["history"]
+    else:
+        assert rel_max(a, b) < 1e-5
+    # the device-side tick reproduces the host formula: alpha_t of step 12
+    m = ia["model"]
+    b1p, b2p = np.float32(1), np.float32(1)
+    for _ in range(12):
+        b1p = np.float32(b1p * np.float32(0.9)); b2p = np.float32(b2p * np.float32(0.999))
+    alpha = np.float32(0.005) * np.sqrt(np.float32(1) - b2p) / (np.float32(1) - b1p)
+    h = m.hyper.cpu().numpy()
+    assert h[0] == b1p and h[1] == b2p and abs(h[2] - alpha) <= 1e-9
