@@ -342,42 +342,30 @@ def run_b200(args):
         # Every step's windows come from pinned host memory.  The upload of step k+1 runs on a copy stream
         # into the other of two device buffer sets while step k computes (input double-buffering); the timed
         # region contains every copy and the per-step device->host read of the accuracies.
-        pins = [t.cpu().pin_memory() for t in (model.rowptr, model.gene, model.label)]
-        bufs = [[model.rowptr, model.gene, model.label], [torch.empty_like(t) for t in (model.rowptr, model.gene, model.label)]]
-        copy_stream = torch.cuda.Stream(device=dev)
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        freed = [torch.cuda.Event(), torch.cuda.Event()]
-
-        def upload(k):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[k])                # the step that last read this buffer set is done
-                for d_, h_ in zip(bufs[k], pins):
-                    d_.copy_(h_, non_blocking=True)
-                ready[k].record(copy_stream)
+        orig = (model.rowptr, model.gene, model.label)
+        feeder = g2v.WindowFeeder(model, *orig)
 
         def e2e_run(n):
-            for k in (0, 1):
-                freed[k].record(torch.cuda.current_stream())
-            upload(0)
+            feeder.upload(0)
             for i in range(n):
                 k = i & 1
                 if i + 1 < n:
-                    upload(k ^ 1)
-                torch.cuda.current_stream().wait_event(ready[k])
-                model.rowptr, model.gene, model.label = bufs[k]
+                    feeder.upload(k ^ 1)
+                feeder.use(k)
                 cbow_step()
-                freed[k].record(torch.cuda.current_stream())
+                feeder.release(k)
                 torch.cuda.current_stream().synchronize()       # the accuracies are on the host
         e2e_run(2)
         barrier(); t0 = time.perf_counter()
         e2e_run(K)
         barrier(); dt = allmax((time.perf_counter() - t0) / K)
-        model.rowptr, model.gene, model.label = bufs[0]
+        model.rowptr, model.gene, model.label = orig
         e2e = {"value": n_tr_tot / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(sum(p.numel() * p.element_size() for p in pins)),
+               "h2d_bytes_per_step": feeder.h2d_bytes,
                "d2h_bytes_per_step": 32,
-               "api": "g2vec_b200.CbowModel step (C ABI kernels); every step's windows are uploaded from pinned host "
-                      "memory (double-buffered on a copy stream) and the accuracies are read back every step"}
+               "api": "g2vec_b200.CbowModel step (C ABI kernels) fed by g2vec_b200.WindowFeeder: every step's windows "
+                      "are uploaded from pinned host memory (double-buffered on a copy stream, gene ids as int16 when "
+                      "n_genes <= 32768) and the accuracies are read back every step"}
 
     clocks = sampler.stop() if sampler else None
     total_launches = _capi.launch_count() - launches0

@@ -231,6 +231,55 @@ class CbowModel:
         return float(acc_host[:1].view(torch.float64)[0])
 
 
+class WindowFeeder:
+    """Feeds a CbowModel's context windows from pinned host memory, double-buffered.
+
+    ``upload(k)`` enqueues, on a private copy stream, the host->device copies of the window CSR into buffer
+    set k (gene ids travel as int16 when n_genes <= 32768 and are widened to int32 on the device: half the
+    PCIe bytes); ``use(k)`` makes the compute stream wait for that upload and points the model at buffer set
+    k; ``release(k)`` marks the set free once the step that read it has been enqueued."""
+
+    def __init__(self, model, rowptr, gene, label):
+        self.m = model
+        dev = model.device
+        to_np = lambda a: a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+        rp, ge, la = to_np(rowptr).astype(np.int32), to_np(gene), to_np(label).astype(np.uint8)
+        self.narrow = model.V <= 32768
+        ge = ge.astype(np.int16 if self.narrow else np.int32)
+        self.pins = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (rp, ge, la)]
+        mk = lambda: [torch.empty(rp.shape[0], dtype=torch.int32, device=dev),
+                      torch.empty(ge.shape[0], dtype=torch.int32, device=dev),
+                      torch.empty(la.shape[0], dtype=torch.uint8, device=dev)]
+        self.bufs = [mk(), mk()]
+        self.stage = [torch.empty(ge.shape[0], dtype=torch.int16, device=dev) for _ in (0, 1)] if self.narrow else None
+        self.stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.freed = [torch.cuda.Event(), torch.cuda.Event()]
+        for k in (0, 1):
+            self.freed[k].record(torch.cuda.current_stream(dev))
+        self.h2d_bytes = int(sum(p.numel() * p.element_size() for p in self.pins))
+
+    def upload(self, k):
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.freed[k])            # the step that last read this set is done
+            b = self.bufs[k]
+            b[0].copy_(self.pins[0], non_blocking=True)
+            if self.narrow:
+                self.stage[k].copy_(self.pins[1], non_blocking=True)
+                b[1].copy_(self.stage[k])                    # int16 -> int32 on the device
+            else:
+                b[1].copy_(self.pins[1], non_blocking=True)
+            b[2].copy_(self.pins[2], non_blocking=True)
+            self.ready[k].record(self.stream)
+
+    def use(self, k):
+        torch.cuda.current_stream(self.m.device).wait_event(self.ready[k])
+        self.m.rowptr, self.m.gene, self.m.label = self.bufs[k]
+
+    def release(self, k):
+        self.freed[k].record(torch.cuda.current_stream(self.m.device))
+
+
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -350,3 +350,29 @@ def test_graph_replayed_steps_equal_eager_steps(g2v, algo):
     alpha = np.float32(0.005) * np.sqrt(np.float32(1) - b2p) / (np.float32(1) - b1p)
     h = m.hyper.cpu().numpy()
     assert h[0] == b1p and h[1] == b2p and abs(h[2] - alpha) <= 1e-9
+
+
+def test_window_feeder_double_buffered_uploads(g2v):
+    """Feeding the windows from pinned host memory (int16 gene ids on the wire, two device buffer sets)
+    gives the same step results as resident windows."""
+    import torch
+    V, N, D = 400, 3000, 128
+    rowptr, gene, label = helpers.random_windows(N, V, 1, 50, seed=21)
+    W0, Wo0 = helpers.init_weights(V, D, 1)
+    win = torch.arange(N, dtype=torch.int32, device="cuda")
+    a = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, algo="rank1"); a.prepare_csc(win)
+    b = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, algo="rank1"); b.prepare_csc(win)
+    feeder = g2v.WindowFeeder(b, rowptr, gene, label)
+    assert feeder.narrow and feeder.h2d_bytes == 4 * (N + 1) + 2 * len(gene) + N
+    feeder.upload(0)
+    for i in range(4):
+        k = i & 1
+        if i < 3:
+            feeder.upload(k ^ 1)
+        feeder.use(k)
+        for m in (a, b):
+            m.acc.zero_(); m.fwdbwd(win, N); m.update(); m.evaluate(win, 2)
+        feeder.release(k)
+        torch.cuda.synchronize()
+        assert (a.acc.cpu() == b.acc.cpu()).all()
+    assert (a.W_ih == b.W_ih).all()
