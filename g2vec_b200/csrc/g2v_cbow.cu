@@ -4,7 +4,9 @@
 // multi-hot X [N, V] (99.7 % zeros) and lets TF1 autodiff + ApplyAdam train W_ih, W_ho
 // (G2Vec.py:239-246).  Here X is CSR (window -> gene ids) and one warp owns one window:
 //
-//   cbow_rows_kernel<VEC, BACKWARD>      D = 128*VEC, each lane owns VEC float4 of the row
+//   cbow_rows_kernel<VEC, BACKWARD, SCATTER_TMA, GATHER_TMA>
+//                                         D = 128*VEC, each lane owns VEC float4 of the row; the two TMA
+//                                         flags select the measured-and-not-shipped staged variants (4.4)
 //     gather   h   = sum_{g in window} W_ih[g, :]          (512*VEC B coalesced per row, 8 rows in flight)
 //     logit    o   = <h, W_ho>                            (warp shuffle reduction)
 //     loss/acc     max(o,0) - o*y + log1p(exp(-|o|)),  (o > 0) == y
@@ -13,6 +15,8 @@
 //              g_ho       += h * dO                       (registers -> smem -> one atomic per CTA)
 //   cbow_update_kernel                    dense epilogue over [V*D] (+[D]): TF1 Adam or SGD,
 //                                         float4, zeroes the gradient for the next step
+//   adam_tick_kernel                      TF1's beta1_power / beta2_power / alpha_t kept on the device so
+//                                         that a whole step can be replayed as one CUDA graph
 //
 // No tensor cores: the 128..512-wide reduction is a memory-bound gather/scatter, not a dense
 // contraction.  Algorithmic bytes per window: l*(8D+4)+5, per step + 32*V*D (Adam).

@@ -12,8 +12,10 @@
 // request).  Per warp in shared memory: the path (L ints, written back once, coalesced) and
 // the visited set -- a V-bit bitmap (one LDS per neighbour) while 8 warps' bitmaps fit in 56 KB
 // (V <= ~46k at L = 80), otherwise an open-addressing hash set of >= 3L slots whose size is
-// independent of V (200k-node graphs keep full occupancy).  Neighbour chunks are kept in registers between the two passes
-// (total, then selection); rows longer than 32*KC neighbours re-read the tail (L1/L2 hits).
+// independent of V (200k-node graphs keep full occupancy).  KC (2 or 4) neighbour chunks are kept in
+// registers between the two passes (per-chunk totals with REDUX.SUM, then one scan inside the selected
+// chunk); rows longer than 32*KC neighbours re-read the tail (L1/L2 hits).  Philox draws are evaluated
+// 32 steps at a time, one step per lane.
 // Walkers are handed out by an atomic ticket so that warps whose walker dead-ends early
 // (62 % of ex_* start nodes have no out-edge) immediately take the next one.
 //
@@ -32,8 +34,6 @@ __device__ __forceinline__ uint32_t hash_slot(int32_t c, int shift) {
     return ((uint32_t)c * 2654435761u) >> shift;
 }
 
-// true if node c is in the warp's visited set.  BITMAP: hs is a V-bit bitmap (1 LDS);
-// otherwise an open-addressing hash set of node ids (-1 = empty).
 // Returns q if node c is NOT in the visited set, else 0.  `hs` indexes the dynamic shared array (kept as
 // an integer offset so that every access is a plain LDS/STS with a register offset).
 extern __shared__ int32_t g2v_walk_smem[];
