@@ -51,7 +51,7 @@ def test_argument_errors_are_reported_not_crashed(g2v):
     assert b"lenPath" in lib.g2v_last_error()
     assert lib.g2v_cbow_fwdbwd(0, 0, 0, 0, 0, 5, 1.0, 0, 0, 0, 0, 0, 0, 10, 128, 0, 0) != 0
     assert b"null pointer" in lib.g2v_last_error()
-    assert lib.g2v_cbow_update(1, 1, 1, 1, 1, 1, 1, 1, 10, 128, 7, 0.1, 0.9, 0.999, 1e-8, 1, 0) != 0
+    assert lib.g2v_cbow_update(1, 1, 1, 1, 1, 1, 1, 1, 10, 128, 7, 0.1, 0.9, 0.999, 1e-8, 1, 0, 0) != 0
     assert b"unknown optimizer" in lib.g2v_last_error()
     with pytest.raises(RuntimeError):
         g2v.CbowModel(np.array([0, 1]), np.array([0]), np.array([0]), 4, 128, np.zeros((4, 128), np.float32),
