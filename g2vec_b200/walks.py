@@ -102,7 +102,9 @@ def generate_paths_host(rowptr, col, qw, len_path, reps, seed=0, group=0, walker
     V = rowptr.shape[0] - 1
     end = V * reps if walker_end is None else walker_end
     n = num_walkers(V, reps, walker_begin, end, walker_stride)
-    nodes = np.empty((n, len_path), dtype=np.int32); lens = np.empty(n, dtype=np.int32)
+    # page-locked result buffers: the device->host copy of the rows then runs at PCIe speed
+    nodes = torch.empty((n, len_path), dtype=torch.int32, pin_memory=True).numpy()
+    lens = torch.empty((n,), dtype=torch.int32, pin_memory=True).numpy()
     rc = lib.g2v_walk_host(rowptr.ctypes.data, col.ctypes.data, qw.ctypes.data, V, col.shape[0], int(len_path),
                            int(seed) & (2**64 - 1), int(group), int(walker_begin), int(end), int(walker_stride),
                            nodes.ctypes.data, lens.ctypes.data)
