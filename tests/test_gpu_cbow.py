@@ -376,3 +376,40 @@ def test_window_feeder_double_buffered_uploads(g2v):
         torch.cuda.synchronize()
         assert (a.acc.cpu() == b.acc.cpu()).all()
     assert (a.W_ih == b.W_ih).all()
+
+
+def test_cbow_full_size_properties(g2v):
+    """BASELINE configs[1] size (10k genes, 200k windows of 80 genes, 128-dim): size-independent properties.
+    (1) linearity: the gradient of all training windows = sum of the gradients of two halves (same 1/N);
+    (2) the row formulation and the collapsed one train to the same vectors; (3) oracle equality on a
+    2000-window sample of the same data; (4) accuracy counters of fwd+bwd equal those of the eval kernel."""
+    import torch
+    V, N, D, Lw = 10_000, 200_000, 128, 80
+    rs = np.random.RandomState(777)
+    gene = np.stack([rs.choice(V, Lw, replace=False) for _ in range(2000)])      # 2000 base windows ...
+    gene = np.tile(gene, (N // 2000, 1))                                         # ... relabelled 100 times
+    perm = rs.permutation(V)
+    gene = np.sort((perm[gene] + (np.arange(N) // 2000)[:, None] * 37) % V, axis=1).astype(np.int32)   # distinct rows
+    rowptr = (np.arange(N + 1) * Lw).astype(np.int32)
+    label = (rs.rand(N) < 0.5).astype(np.uint8)
+    W0, Wo0 = helpers.init_weights(V, D, 5)
+    m = g2v.CbowModel(rowptr, gene.ravel(), label, V, D, W0, Wo0)
+    m.fwdbwd(None, N, win_begin=0, n_win=N); torch.cuda.synchronize()
+    full = m.g_ih.clone(); full_ho = m.g_ho.clone(); acc_full = m.acc.cpu().clone()
+    m.g_ih.zero_(); m.g_ho.zero_(); m.acc.zero_()
+    m.fwdbwd(None, N, win_begin=0, n_win=N // 2); m.fwdbwd(None, N, win_begin=N // 2, n_win=N - N // 2)
+    m.evaluate(None, 2, win_begin=0, n_win=N); torch.cuda.synchronize()
+    assert float((m.g_ih - full).abs().max()) <= 2e-5 * float(full.abs().max())
+    assert float((m.g_ho - full_ho).abs().max()) <= 2e-5 * float(full_ho.abs().max())
+    acc = m.acc.cpu()
+    assert int(acc[1]) == int(acc_full[1]) == int(acc[2])                    # (4)
+    sample = np.sort(rs.choice(N, 2000, replace=False)).astype(np.int64)
+    o_gih, o_gho, _, o_nc = oracle.cbow_grad(rowptr, gene.ravel(), label, sample, N, W0, Wo0)
+    m.g_ih.zero_(); m.g_ho.zero_(); m.acc.zero_()
+    m.fwdbwd(torch.from_numpy(sample.astype(np.int32)).cuda(), N); torch.cuda.synchronize()
+    assert rel_max(m.g_ih.cpu().numpy(), o_gih) < 2e-5 and abs(int(m.acc.cpu()[1]) - o_nc) <= 1
+    tr = np.arange(N, dtype=np.int64)[: int(N * 0.8)]; va = np.arange(N, dtype=np.int64)[int(N * 0.8):]
+    kw = dict(max_epoch=3, seed=0, W_ih0=W0, W_ho0=Wo0, split=(tr, va), early_stop=False, log=None)
+    a = g2v.train_cbow(rowptr, gene.ravel(), label, V, D, 0.005, algo="rows", **kw)
+    b = g2v.train_cbow(rowptr, gene.ravel(), label, V, D, 0.005, algo="rank1", **kw)
+    assert rel_max(a, b) < RTOL_VEC
