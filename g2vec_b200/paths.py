@@ -4,7 +4,8 @@ common to both groups, emit CSR context windows, and the gene-frequency vote.
 Reference: ``tuple(sorted(path))`` into a set (G2Vec.py:345,351), ``integrate_pathSet``
 (:310-322, dense int32 [n_paths, n_genes+1]) and ``count_geneFreq`` (:288-308).  Here paths stay on
 the device as padded sorted rows and the dense multi-hot matrix (1.37 GB at ex_* scale) is never
-built: the trainer consumes CSR windows.  torch sort/unique are used as plumbing.
+built: the trainer consumes CSR windows.  Row sorting and the exact duplicate / cross-group tests are
+csrc/g2v_paths.cu; the 8-byte key sort, the compaction and the prefix sums are torch plumbing.
 """
 import numpy as np
 import torch
@@ -12,12 +13,42 @@ import torch
 PAD = 2**31 - 1
 
 
+def _canon(nodes):
+    """csrc/g2v_paths.cu: every row sorted ascending (PAD at the end) + a 64-bit key per row."""
+    from . import _capi
+    lib = _capi.load()
+    nodes = nodes.contiguous()
+    n, L = nodes.shape
+    rows = torch.empty_like(nodes)
+    key = torch.empty((n,), dtype=torch.int64, device=nodes.device)
+    st = torch.cuda.current_stream(nodes.device).cuda_stream
+    _capi.check(lib.g2v_paths_canonicalise(nodes.data_ptr(), n, L, rows.data_ptr(), key.data_ptr(), st),
+                "g2v_paths_canonicalise")
+    return rows, key
+
+
+def _mark(rows, key, group=None):
+    """Key-order visit of the rows; returns (perm, flag) with flag[i] about row perm[i] (see g2v_paths_mark)."""
+    from . import _capi
+    lib = _capi.load()
+    n, L = rows.shape
+    ks, perm = torch.sort(key)                         # radix sort of 8-byte keys (plumbing)
+    flag = torch.empty((n,), dtype=torch.uint8, device=rows.device)
+    st = torch.cuda.current_stream(rows.device).cuda_stream
+    _capi.check(lib.g2v_paths_mark(rows.data_ptr(), ks.data_ptr(), perm.data_ptr(),
+                                   0 if group is None else group.data_ptr(), n, L, flag.data_ptr(), st),
+                "g2v_paths_mark")
+    return perm, flag.bool()
+
+
 def canonical_rows(nodes, lens=None):
-    """Walk rows (visit order, -1 padded) -> unique rows, each sorted ascending, PAD-padded;
-    rows themselves in lexicographic order (the set of G2Vec.py:351)."""
-    rows = torch.where(nodes < 0, torch.full_like(nodes, PAD), nodes)
-    rows, _ = torch.sort(rows, dim=1)
-    return torch.unique(rows, dim=0)
+    """Walk rows (visit order, -1 padded) -> the set of G2Vec.py:345,351: unique rows, each sorted ascending
+    and PAD-padded.  Row order: ascending key (arbitrary but deterministic)."""
+    if nodes.shape[0] == 0:
+        return torch.empty_like(nodes)
+    rows, key = _canon(nodes)
+    perm, first = _mark(rows, key)
+    return rows[perm[first]]
 
 
 def integrate(rows_good, rows_poor):
@@ -32,12 +63,15 @@ def integrate(rows_good, rows_poor):
         return torch.cat([r, pad], dim=1)
 
     a, b = widen(rows_good), widen(rows_poor)
-    both = torch.cat([a, b], dim=0)
+    both = torch.cat([a, b], dim=0).contiguous()
     lab = torch.cat([torch.zeros(a.shape[0], dtype=torch.uint8, device=a.device),
                      torch.ones(b.shape[0], dtype=torch.uint8, device=b.device)])
-    _, inv, cnt = torch.unique(both, dim=0, return_inverse=True, return_counts=True)
-    keep = cnt[inv] == 1                       # each group's rows are already unique
-    return both[keep], lab[keep]
+    if both.shape[0] == 0:
+        return both, lab
+    _, key = _canon(both)                              # rows are already sorted: this only makes the keys
+    perm, survives = _mark(both, key, group=lab)
+    idx, _ = torch.sort(perm[survives])                # back to input order: good rows first
+    return both[idx], lab[idx]
 
 
 def windows_csr(rows, labels):

@@ -178,6 +178,21 @@ int g2v_pcc_edge_weights(const float *z, int32_t S, int32_t V, const int32_t *sr
                          int64_t E, float *w, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Between the two hot paths: `tuple(sorted(path))` into a set (G2Vec.py:345,351) and
+ * the removal of paths common to both groups (G2Vec.py:313).
+ * g2v_paths_canonicalise: row i of nodes [n*L] (-1 or INT32_MAX padded) -> sorted [n*L] ascending with
+ *   INT32_MAX padding, and a non-negative 64-bit key per row (equal rows => equal keys).
+ * g2v_paths_mark: rows visited in key order (key_sorted[i] = key[perm[i]], ascending).  group == NULL:
+ *   flag[i] = 1 iff row perm[i] is the first occurrence of its content (set semantics, exact: rows of a key
+ *   run are compared in full).  group != NULL (0/1 per row): flag[i] = 1 iff no row of the other group has
+ *   the same content (the row survives `pathSet - commonPath`).
+ * ------------------------------------------------------------------------------------- */
+int g2v_paths_canonicalise(const int32_t *nodes, int64_t n, int32_t L, int32_t *sorted, int64_t *key,
+                           void *stream);
+int g2v_paths_mark(const int32_t *rows, const int64_t *key_sorted, const int64_t *perm, const uint8_t *group,
+                   int64_t n, int32_t L, uint8_t *flag, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Test hooks (used by tests/ only): 64-bit draws 0..n-1 of one walker subsequence from the
  * kernel's own Philox, and the same words from curand's Philox4_32_10 generator
  * (curand_init(seed, subsequence, 0)), to prove the stream is curand-compatible.

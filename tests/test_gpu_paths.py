@@ -33,3 +33,56 @@ def test_pipeline_equals_oracle_on_ex():
     ps = g2v.generate_pathSet(g2v.WalkGraph(rp, col, weights=w), 80, 1, seed=5, group=0)
     nodes, lens = oracle.walks(rp, col, oracle.quantise_weights(w), 80, 5, 0, 0, len(rp) - 1)
     assert ps == oracle.path_set(nodes, lens)
+
+
+def test_mark_kernel_is_exact_under_key_collisions():
+    """g2v_paths_mark compares full rows inside a key run, so set semantics hold even if different rows share
+    a key: feed it deliberately colliding keys (everything in one run, and 7 runs) and compare with Python sets."""
+    import numpy as np
+    import torch
+    from g2vec_b200 import _capi, paths
+    lib = _capi.load()
+    rs = np.random.RandomState(5)
+    base = [tuple(sorted(rs.choice(40, size=rs.randint(1, 9), replace=False))) for _ in range(60)]
+    picks = [base[i] for i in rs.randint(0, 60, size=400)]
+    L = 8
+    rows = np.full((400, L), paths.PAD, np.int32)
+    for i, p in enumerate(picks):
+        rows[i, :len(p)] = p
+    grp = (rs.rand(400) < 0.5).astype(np.uint8)
+    for nkeys in (1, 7):
+        key = np.array([hash(p) % nkeys for p in picks], dtype=np.int64)        # equal rows -> equal keys
+        r_d = torch.from_numpy(rows).cuda(); k_d = torch.from_numpy(key).cuda(); g_d = torch.from_numpy(grp).cuda()
+        ks, perm = torch.sort(k_d, stable=True)
+        flag = torch.empty(400, dtype=torch.uint8, device="cuda")
+        _capi.check(lib.g2v_paths_mark(r_d.data_ptr(), ks.data_ptr(), perm.data_ptr(), 0, 400, L, flag.data_ptr(), 0), "mark")
+        torch.cuda.synchronize()
+        kept = [picks[i] for i in perm[flag.bool()].cpu().numpy()]
+        assert len(kept) == len(set(kept)) and set(kept) == set(picks)          # first occurrences only, all of them
+        _capi.check(lib.g2v_paths_mark(r_d.data_ptr(), ks.data_ptr(), perm.data_ptr(), g_d.data_ptr(), 400, L,
+                                       flag.data_ptr(), 0), "mark")
+        torch.cuda.synchronize()
+        s0 = {p for p, g in zip(picks, grp) if g == 0}; s1 = {p for p, g in zip(picks, grp) if g == 1}
+        surv = perm[flag.bool()].cpu().numpy()
+        assert {(int(grp[i]), picks[i]) for i in surv} == {(0, p) for p in s0 - s1} | {(1, p) for p in s1 - s0}
+
+
+def test_canonicalise_sorts_rows_of_any_length():
+    import numpy as np
+    import torch
+    from g2vec_b200 import paths
+    rs = np.random.RandomState(1)
+    for L in (1, 2, 31, 32, 33, 80, 160, 1000):
+        n = 50
+        nodes = np.full((n, L), -1, np.int32)
+        for i in range(n):
+            k = rs.randint(1, L + 1)
+            nodes[i, :k] = rs.choice(5000, size=k, replace=False)
+        nodes[7] = nodes[3]                                   # a duplicate in a different visit order
+        nodes[7, :(nodes[3] >= 0).sum()] = rs.permutation(nodes[3][nodes[3] >= 0])
+        rows, key = paths._canon(torch.from_numpy(nodes).cuda())
+        rows = rows.cpu().numpy(); key = key.cpu().numpy()
+        want = np.sort(np.where(nodes < 0, paths.PAD, nodes), axis=1)
+        assert (rows == want).all() and (key >= 0).all() and key[7] == key[3]
+        uniq = paths.canonical_rows(torch.from_numpy(nodes).cuda())
+        assert paths.rows_to_set(uniq) == {tuple(int(x) for x in r[r != paths.PAD]) for r in want}
