@@ -209,16 +209,15 @@ def run_b200(args):
     walk_ms = allmax(float(np.mean(wt)))
     visits_loc = int(sum(int(o[1].sum()) for o in outs))
     visits = allsum(visits_loc)
-    # algorithmic bytes of one pass: per visit 4 B (node id written); per visit that is expanded (every visit
-    # but the L-th of a full-length walk) 8 B rowptr + 4 B per neighbour (the row's prefix sums) + 4 B row total
-    # + 4 B for the one col entry of the accepted attempt
+    # algorithmic bytes of one pass: per visit 4 B (node id written); per visit that scans its row
+    # (every visit but the L-th of a full-length walk) 8 B rowptr + 8 B per neighbour (col + weight)
     wbytes = 0
     for g in (0, 1):
         nodes, lens = outs[g]
         deg = (graphs[g].rowptr[1:] - graphs[g].rowptr[:-1]).to(torch.int64)
         scan = nodes[:, :L - 1] if L > 1 else nodes[:, :0]
         m = scan >= 0
-        wbytes += int(lens.sum()) * 4 + int(m.sum()) * 16 + 4 * int(deg[scan[m].to(torch.int64)].sum())
+        wbytes += int(lens.sum()) * 4 + int(m.sum()) * 8 + 8 * int(deg[scan[m].to(torch.int64)].sum())
     walk_gbs = wbytes / (float(np.mean(wt)) * 1e-3) / 1e9
 
     walk_e2e = None
@@ -420,8 +419,7 @@ def run_b200(args):
                                   "unit": "GB/s", "frac": walk_gbs / peak,
                                   "traffic": traffic_lookup("walk", args.workload),
                                   "algorithmic_bytes_per_pass": wbytes,
-                                  "bytes_model": "4 B per visit + (16 + 4*deg) B per expanded visit (rowptr, row prefix sums, row total, "
-                                                 "one col entry)"},
+                                  "bytes_model": "4 B per visit + (8 + 8*deg) B per visit that scans its row"},
                      "e2e": walk_e2e, "cpu_baseline": walk_cpu},
         }
         print(json.dumps(line))

@@ -24,22 +24,6 @@ def quantise_weights(w):
     return q.astype(np.uint32)
 
 
-def row_prefix_sums(rowptr, q):
-    """Inclusive prefix sums of the quantised weights INSIDE each CSR row (uint32) -- what the walk sampler
-    reads: the last entry of a row is the row's total weight, which must stay below 2^32."""
-    rowptr = np.asarray(rowptr, dtype=np.int64)
-    q = np.asarray(q, dtype=np.uint64)
-    if q.size == 0:
-        return np.zeros(0, dtype=np.uint32)
-    c = np.cumsum(q, dtype=np.uint64)
-    starts = rowptr[:-1]
-    base = np.where(starts > 0, c[np.maximum(starts, 1) - 1], 0).astype(np.uint64)
-    p = c - np.repeat(base, np.diff(rowptr))
-    if p.max() >= 2**32:
-        raise ValueError("a row's total quantised weight exceeds 2^32 (degree x weight too large)")
-    return p.astype(np.uint32)
-
-
 def csr_from_edges(src, dst, w, V):
     """Directed edges -> CSR sorted by (src, dst).  A duplicated (src, dst) keeps the LAST
     weight, as repeated assignment to adjMat[src][dest] does (G2Vec.py:390)."""

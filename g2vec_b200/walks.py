@@ -25,9 +25,8 @@ def _to_dev(a, dtype, device):
 
 
 class WalkGraph:
-    """One group's directed weighted graph resident in HBM as CSR: rowptr int32 [V+1], col int32 [E]
-    ascending per row, psum uint32 [E] (stored as int32 bits) = inclusive prefix sums, inside each row, of the
-    weights quantised to integers (q = rint(w * 2^16)); ``qw`` keeps the quantised weights themselves."""
+    """One group's directed weighted graph resident in HBM as CSR
+    (rowptr int32 [V+1], col int32 [E] ascending per row, qw uint32 [E] stored as int32 bits)."""
 
     def __init__(self, rowptr, col, weights=None, qw=None, device=None):
         device = _dev(device)
@@ -53,17 +52,6 @@ class WalkGraph:
         self.E = int(self.col.shape[0])
         if self.qw.shape[0] != self.E:
             raise ValueError("col / weight length mismatch")
-        # per-row inclusive prefix sums on the device (same rule as graph.row_prefix_sums)
-        q64 = self.qw.to(torch.int64) & 0xFFFFFFFF
-        if self.E and (int(q64.min()) < 1 or int(q64.max()) > _graph.Q_MAX):
-            raise ValueError("quantised weights must be in [1, 2^24]")
-        c = torch.cumsum(q64, dim=0)
-        starts = self.rowptr[:-1].to(torch.int64)
-        base = torch.where(starts > 0, c[torch.clamp(starts, min=1) - 1] if self.E else starts, torch.zeros_like(starts))
-        p = c - torch.repeat_interleave(base, (self.rowptr[1:] - self.rowptr[:-1]).to(torch.int64))
-        if self.E and int(p.max()) >= 2**32:
-            raise ValueError("a row's total quantised weight exceeds 2^32 (degree x weight too large)")
-        self.psum = torch.where(p >= 2**31, p - 2**32, p).to(torch.int32)     # uint32 bits in an int32 tensor
         self.device = device
         self._ws = torch.zeros(max(int(_capi.load().g2v_walk_workspace_bytes()), 8), dtype=torch.uint8, device=device)
 
@@ -73,7 +61,7 @@ class WalkGraph:
         return cls(rp, col, weights=w, device=device)
 
     def nbytes(self):
-        return 4 * (self.V + 1) + 8 * self.E       # rowptr + col + psum
+        return 4 * (self.V + 1) + 8 * self.E
 
 
 def num_walkers(V, reps, begin=0, end=None, stride=1):
@@ -98,7 +86,7 @@ def generate_paths(g, len_path, reps, seed=0, group=0, walker_begin=0, walker_en
         assert nodes.shape == (n, len_path) and lens.shape == (n,) and nodes.is_contiguous()
     with torch.cuda.device(g.device):
         st = torch.cuda.current_stream().cuda_stream
-        rc = lib.g2v_walk_launch(g.rowptr.data_ptr(), g.col.data_ptr(), g.psum.data_ptr(), g.V, g.E, int(len_path),
+        rc = lib.g2v_walk_launch(g.rowptr.data_ptr(), g.col.data_ptr(), g.qw.data_ptr(), g.V, g.E, int(len_path),
                                  int(seed) & (2**64 - 1), int(group), int(walker_begin), int(end),
                                  int(walker_stride), nodes.data_ptr(), lens.data_ptr(), g._ws.data_ptr(), st)
     _capi.check(rc, "g2v_walk_launch")
@@ -107,18 +95,17 @@ def generate_paths(g, len_path, reps, seed=0, group=0, walker_begin=0, walker_en
 
 def generate_paths_host(rowptr, col, qw, len_path, reps, seed=0, group=0, walker_begin=0, walker_end=None,
                         walker_stride=1):
-    """Same through ``g2v_walk_host``: NumPy arrays in (qw = quantised weights; the per-row prefix sums the C ABI
-    takes are formed here), NumPy arrays out (the C ABI does the copies)."""
+    """Same through ``g2v_walk_host``: NumPy arrays in, NumPy arrays out (the C ABI does the copies)."""
     lib = _capi.load()
     rowptr = np.ascontiguousarray(rowptr, dtype=np.int32); col = np.ascontiguousarray(col, dtype=np.int32)
-    psum = np.ascontiguousarray(_graph.row_prefix_sums(rowptr, np.ascontiguousarray(qw, dtype=np.uint32)))
+    qw = np.ascontiguousarray(qw, dtype=np.uint32)
     V = rowptr.shape[0] - 1
     end = V * reps if walker_end is None else walker_end
     n = num_walkers(V, reps, walker_begin, end, walker_stride)
     # page-locked result buffers: the device->host copy of the rows then runs at PCIe speed
     nodes = torch.empty((n, len_path), dtype=torch.int32, pin_memory=True).numpy()
     lens = torch.empty((n,), dtype=torch.int32, pin_memory=True).numpy()
-    rc = lib.g2v_walk_host(rowptr.ctypes.data, col.ctypes.data, psum.ctypes.data, V, col.shape[0], int(len_path),
+    rc = lib.g2v_walk_host(rowptr.ctypes.data, col.ctypes.data, qw.ctypes.data, V, col.shape[0], int(len_path),
                            int(seed) & (2**64 - 1), int(group), int(walker_begin), int(end), int(walker_stride),
                            nodes.ctypes.data, lens.ctypes.data)
     _capi.check(rc, "g2v_walk_host")

@@ -52,33 +52,27 @@ int64_t g2v_launch_count(void);
  * G2Vec.py:324-352, for the walkers  w = walker_begin + i*walker_stride < walker_end,
  * w = rep*V + src  (rep = G2Vec.py:348 `step`, src = :349).
  *
- *   rowptr [V+1], col [E] (ascending inside a row = dense row order), psum [E]: CSR of the
- *     group's directed adjacency (rows = out-edges, G2Vec.py:390); psum holds, inside each row,
- *     the INCLUSIVE PREFIX SUMS of the weights quantised to integers (q = rint(|PCC| * 2^16),
- *     1 <= q <= 2^24), so the last entry of a row is the row total, which must be < 2^32.
- *   The draw that replaces np.random.choice (G2Vec.py:341): up to 4 rejection attempts
- *     r = floor(x * T_row / 2^64) -> first neighbour whose prefix exceeds r, accepted if unvisited;
- *     then the exact inverse CDF over the unvisited neighbours (dead end if none).  Same distribution
- *     as the reference (probability proportional to weight among the unvisited neighbours).
+ *   rowptr [V+1], col [E] (ascending inside a row = dense row order), qw [E]: CSR of the
+ *     group's directed adjacency (rows = out-edges, G2Vec.py:390) with weights quantised to
+ *     integers, 1 <= qw <= 2^24  (q = rint(|PCC| * 2^16)).
  *   L: --lenPath, the maximum number of NODES of a path (G2Vec.py:331).  1 <= L <= 4096, and the
  *     per-CTA path + visited-set buffers must fit shared memory: always true for L <= 1365, and
  *     for any L <= 4096 while V <= ~90k (bitmap visited set); otherwise the call fails with a message.
  *   seed/group: Philox4x32-10 key and the high bits of the walker's subsequence
- *     (subsequence = group*2^40 + w; 64-bit draw k = words 2k,2k+1; step s, attempt a uses draw
- *     a*4096 + s), so that any
+ *     (subsequence = group*2^40 + w, 64-bit draw s = words 2s,2s+1), so that any
  *     (walker, step) is addressable independently: results do not depend on sharding.
  *   out_nodes [n*L]: visit order of walker i in row i, padded with -1  (the reference
  *     sorts afterwards, G2Vec.py:345).  out_len [n]: nodes visited.  n = number of walkers.
  *   workspace: >= g2v_walk_workspace_bytes() bytes of device scratch (zeroed by the call).
  * ------------------------------------------------------------------------------------- */
 size_t g2v_walk_workspace_bytes(void);
-int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const uint32_t *psum, int32_t V,
+int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const uint32_t *qw, int32_t V,
                     int64_t E, int32_t L, uint64_t seed, uint32_t group, int64_t walker_begin,
                     int64_t walker_end, int64_t walker_stride, int32_t *out_nodes,
                     int32_t *out_len, void *workspace, void *stream);
 
 /* Same, HOST pointers in and out (allocates, copies, launches, copies back, frees). */
-int g2v_walk_host(const int32_t *rowptr, const int32_t *col, const uint32_t *psum, int32_t V,
+int g2v_walk_host(const int32_t *rowptr, const int32_t *col, const uint32_t *qw, int32_t V,
                   int64_t E, int32_t L, uint64_t seed, uint32_t group, int64_t walker_begin,
                   int64_t walker_end, int64_t walker_stride, int32_t *out_nodes,
                   int32_t *out_len);

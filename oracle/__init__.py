@@ -138,21 +138,8 @@ def walks(rowptr, col, qw, L, seed, group, walker_begin, walker_end, walker_stri
     return nodes, lens
 
 
-WALK_ATTEMPTS = 4      # rejection attempts per step before the exact fallback (g2v_oracle.c)
-WALK_MAXLEN = 4096     # draw index of (step s, attempt a) = a * WALK_MAXLEN + s
-
-
-def _inverse_cdf(pairs, r):
-    acc = 0
-    for c, q in pairs:
-        acc += q
-        if acc > r:
-            return c
-    raise AssertionError("unreachable: r < total")
-
-
 def walks_py(rowptr, col, qw, L, seed, group, walker_ids):
-    """Pure-Python restatement of G2Vec.py:328-346 with the Philox rejection draw (small cases)."""
+    """Pure-Python restatement of G2Vec.py:328-346 with the Philox integer draw (small cases)."""
     V = len(rowptr) - 1
     out = []
     for w in walker_ids:
@@ -164,23 +151,18 @@ def walks_py(rowptr, col, qw, L, seed, group, walker_ids):
             if s == L - 1:
                 break
             seen = set(path)
-            row = [(int(col[j]), int(qw[j])) for j in range(rowptr[cur], rowptr[cur + 1])]
-            if not row:
-                break
-            Tall = sum(q for _, q in row)
-            nxt = None
-            for a in range(WALK_ATTEMPTS):                          # rejection attempts on the whole row
-                c = _inverse_cdf(row, (draw64_py(seed, subseq, a * WALK_MAXLEN + s) * Tall) >> 64)
-                if c not in seen:
-                    nxt = c
+            nb = [(int(col[j]), int(qw[j])) for j in range(rowptr[cur], rowptr[cur + 1])
+                  if int(col[j]) not in seen]                       # :334-336
+            T = sum(q for _, q in nb)                               # :338
+            if T == 0:
+                break                                               # :342-344
+            r = (draw64_py(seed, subseq, s) * T) >> 64
+            acc = 0
+            for c, q in nb:                                         # :341 inverse CDF
+                acc += q
+                if acc > r:
+                    cur = c
                     break
-            if nxt is None:                                         # exact fallback, :334-341
-                nb = [(c, q) for c, q in row if c not in seen]
-                T = sum(q for _, q in nb)                           # :338
-                if T == 0:
-                    break                                           # :342-344
-                nxt = _inverse_cdf(nb, (draw64_py(seed, subseq, WALK_ATTEMPTS * WALK_MAXLEN + s) * T) >> 64)
-            cur = nxt
         out.append(path)
     return out
 

@@ -79,30 +79,19 @@ uint64_t g2v_oracle_draw64(uint64_t seed, uint64_t subseq, uint32_t s) { return 
  *   else: break                              :342-344
  * with at most L appended nodes (:331).  Walker id w = rep*V + src covers
  * `for step in range(iterations): for src in range(n_genes)` (:348-349).
- * The draw (replaces np.random.choice over the masked, renormalised row, G2Vec.py:336-341) is
- * REJECTION SAMPLING followed by an exact fallback -- the accepted neighbour has exactly the
- * reference's distribution (probability proportional to weight among the unvisited ones):
- *   attempts a = 0 .. G2V_WALK_ATTEMPTS-1:
- *       r = floor(x_a * T_all / 2^64),  T_all = total quantised weight of the WHOLE row,
- *       candidate = first neighbour (ascending dest order) whose inclusive prefix sum exceeds r;
- *       accept it if it has not been visited;
- *   fallback (all attempts hit visited nodes): T = total weight of the unvisited neighbours,
- *       dead end if T = 0, else r = floor(x_R * T / 2^64) and the same inverse CDF over the unvisited.
- * x_a is the 64-bit Philox draw number a*G2V_WALK_MAXLEN + s of the walker's subsequence (s = step < L <=
- * G2V_WALK_MAXLEN), so the first attempts of consecutive steps are consecutive draws.
- * Only integer arithmetic: any evaluation order gives the same node.
+ * The draw: T = sum of quantised weights of unvisited out-neighbours (uint64),
+ * r = floor(x * T / 2^64) with x the 64-bit Philox draw, next = first neighbour in
+ * ascending dest order whose inclusive prefix sum exceeds r (inverse CDF, the same rule
+ * as np.random.choice's searchsorted(cdf, u, side='right'), G2Vec.py:341).
  * Output keeps VISIT ORDER (the reference sorts afterwards, :345); rows are padded
  * with -1.  Returns 0, or -1 on bad arguments.
  * ---------------------------------------------------------------------------------- */
-#define G2V_WALK_ATTEMPTS 4
-#define G2V_WALK_MAXLEN 4096u
-
 int g2v_oracle_walks(const int32_t *rowptr, const int32_t *col, const uint32_t *qw,
                      int32_t V, int32_t L, uint64_t seed, uint32_t group,
                      int64_t walker_begin, int64_t walker_end, int64_t walker_stride,
                      int32_t *out_nodes, int32_t *out_len)
 {
-    if (V <= 0 || L <= 0 || L > (int32_t)4096 || walker_stride <= 0 || walker_begin < 0) return -1;
+    if (V <= 0 || L <= 0 || walker_stride <= 0 || walker_begin < 0) return -1;
     uint8_t *visited = (uint8_t *)calloc((size_t)V, 1);
     if (!visited) return -1;
     int64_t slot = 0;
@@ -116,32 +105,18 @@ int g2v_oracle_walks(const int32_t *rowptr, const int32_t *col, const uint32_t *
             visited[cur] = 1;
             if (s == L - 1) break;      /* the reference's last draw is never appended */
             int32_t b = rowptr[cur], e = rowptr[cur + 1];
-            if (b == e) break;          /* no out-edges: dead end */
-            uint64_t Tall = 0;
-            for (int32_t j = b; j < e; ++j) Tall += qw[j];
+            uint64_t T = 0;
+            for (int32_t j = b; j < e; ++j)
+                if (!visited[col[j]]) T += qw[j];
+            if (T == 0) break;          /* dead end */
+            uint64_t x = draw64(seed, subseq, (uint32_t)s);
+            uint64_t r = (uint64_t)(((unsigned __int128)x * T) >> 64);
+            uint64_t acc = 0;
             int32_t nxt = -1;
-            for (int a = 0; a < G2V_WALK_ATTEMPTS && nxt < 0; ++a) {
-                uint64_t x = draw64(seed, subseq, (uint32_t)a * G2V_WALK_MAXLEN + (uint32_t)s);
-                uint64_t r = (uint64_t)(((unsigned __int128)x * Tall) >> 64);
-                uint64_t acc = 0;
-                for (int32_t j = b; j < e; ++j) {
-                    acc += qw[j];
-                    if (acc > r) { if (!visited[col[j]]) nxt = col[j]; break; }
-                }
-            }
-            if (nxt < 0) {              /* exact fallback over the unvisited neighbours */
-                uint64_t T = 0;
-                for (int32_t j = b; j < e; ++j)
-                    if (!visited[col[j]]) T += qw[j];
-                if (T == 0) break;      /* dead end: every neighbour already visited */
-                uint64_t x = draw64(seed, subseq, G2V_WALK_ATTEMPTS * G2V_WALK_MAXLEN + (uint32_t)s);
-                uint64_t r = (uint64_t)(((unsigned __int128)x * T) >> 64);
-                uint64_t acc = 0;
-                for (int32_t j = b; j < e; ++j) {
-                    if (visited[col[j]]) continue;
-                    acc += qw[j];
-                    if (acc > r) { nxt = col[j]; break; }
-                }
+            for (int32_t j = b; j < e; ++j) {
+                if (visited[col[j]]) continue;
+                acc += qw[j];
+                if (acc > r) { nxt = col[j]; break; }
             }
             cur = nxt;                  /* always found: r < T */
         }

@@ -74,43 +74,29 @@ class LegacyDraw:
         self.V = V
         self.rng = np.random.RandomState(seed)
 
-    def __call__(self, walker, step, cols, weights, seen):
-        keep = [i for i, c in enumerate(cols) if c not in seen]
+    def __call__(self, walker, step, cols, weights):
         prob = np.zeros(self.V, dtype=np.float32)
-        prob[[cols[i] for i in keep]] = [weights[i] for i in keep]
+        prob[cols] = weights
         z = prob.sum()
         prob /= z
         return int(self.rng.choice(self.V, size=1, p=prob)[0])
 
 
 class PhiloxIntDraw:
-    """The oracle/GPU rule: up to `attempts` rejection draws over the whole row
-    (r = floor(x*T_all/2^64), first inclusive prefix > r, accepted if unvisited), then the exact
-    inverse CDF over the unvisited neighbours.  Draw index = attempt*4096 + step."""
+    """The oracle/GPU rule: r = floor(x*T/2^64), first inclusive prefix > r."""
 
-    def __init__(self, seed, group, draw64, attempts=4):
-        self.seed, self.group, self.draw64, self.attempts = seed, group, draw64, attempts
+    def __init__(self, seed, group, draw64):
+        self.seed, self.group, self.draw64 = seed, group, draw64
 
-    @staticmethod
-    def _pick(cols, q, r):
+    def __call__(self, walker, step, cols, q):
+        T = int(sum(int(x) for x in q))
+        r = (self.draw64(self.seed, (self.group << 40) + int(walker), step) * T) >> 64
         acc = 0
         for c, x in zip(cols, q):
             acc += int(x)
             if acc > r:
                 return int(c)
-        raise AssertionError("unreachable: r < total")
-
-    def __call__(self, walker, step, cols, q, seen):
-        sub = (self.group << 40) + int(walker)
-        Tall = int(sum(int(x) for x in q))
-        for a in range(self.attempts):
-            c = self._pick(cols, q, (self.draw64(self.seed, sub, a * 4096 + step) * Tall) >> 64)
-            if c not in seen:
-                return c
-        keep = [i for i, c in enumerate(cols) if c not in seen]
-        T = int(sum(int(q[i]) for i in keep))
-        return self._pick([cols[i] for i in keep], [q[i] for i in keep],
-                          (self.draw64(self.seed, sub, self.attempts * 4096 + step) * T) >> 64)
+        raise AssertionError("unreachable: r < T")
 
 
 def walks_generic(rowptr, col, w, L, walker_ids, draw, consume_last=False):
@@ -131,7 +117,7 @@ def walks_generic(rowptr, col, w, L, walker_ids, draw, consume_last=False):
                 break
             if s == L - 1 and not consume_last:
                 break
-            cur = draw(wid, s, [int(col[j]) for j in range(lo, hi)], [w[j] for j in range(lo, hi)], seen)
+            cur = draw(wid, s, [int(col[j]) for j in keep], [w[j] for j in keep])
         out.append(path)
     return out
 

@@ -69,8 +69,7 @@ def test_ex_graph_bit_exact(g2v, L):
 
 
 def test_high_degree_rows_take_the_tail_path(g2v):
-    """Rows with more than 128 neighbours (register cache = 2 or 4 chunks of 32) and a complete graph, where the
-    late steps reject almost every attempt and take the exact fallback."""
+    """Rows with more than 128 neighbours (register cache = 4 chunks of 32) and a complete graph."""
     V = 400
     A = np.zeros((V, V), dtype=np.float32)
     rs = np.random.RandomState(3)
@@ -154,11 +153,11 @@ def test_hash_visited_set_path(g2v, monkeypatch):
     assert (got == want).all() and (gl == wl).all() and wl.max() == 80 and wl.min() == 1
 
 
-@pytest.mark.parametrize("kc", ["2", "4"])
+@pytest.mark.parametrize("tile,kc", [("8", "4"), ("16", "4"), ("32", "4"), ("32", "2")])
 @pytest.mark.parametrize("vis", ["bitmap", "hash"])
-def test_every_kernel_instantiation_is_bit_exact(g2v, monkeypatch, kc, vis):
-    """2/4 register-cached prefix chunks x bitmap/hash visited set, on graphs that exercise the rejection
-    attempts, the exact fallback (small dense components) and the tail path (rows of 299 neighbours)."""
+def test_every_tile_width_and_visited_set_is_bit_exact(g2v, monkeypatch, tile, kc, vis):
+    """Every kernel instantiation: 8/16/32 lanes per walker x 2/4 register-cached chunks x bitmap/hash."""
+    monkeypatch.setenv("G2V_WALK_TILE", tile)
     monkeypatch.setenv("G2V_WALK_KC", kc)
     monkeypatch.setenv("G2V_WALK_VISITED", vis)
     cases = [helpers.ex_graph(1) + (80, 2), helpers.random_graph(2000, 40, seed=1, dead_frac=0.2) + (33, 3)]
