@@ -56,3 +56,25 @@ def test_quantisation_error_is_far_below_sampling_noise():
     q = oracle.quantise_weights(w).astype(np.float64)
     p, pq = w.astype(np.float64) / w.sum(dtype=np.float64), q / q.sum()
     assert np.abs(p - pq).max() / p.min() < 2e-5
+
+
+def test_distribution_on_a_dense_graph_where_most_neighbours_are_visited():
+    """A small dense graph: late in a walk most neighbours are already visited, so the masked renormalised
+    draw matters.  Node-at-position distributions must match the reference's draw."""
+    rs = np.random.RandomState(8)
+    V = 10
+    A = ((rs.rand(V, V) < 0.85) * (0.5 + 0.5 * rs.rand(V, V))).astype(np.float32)
+    np.fill_diagonal(A, 0)
+    rp, col, w = legacy.csr_from_dense(A)
+    q = oracle.quantise_weights(w)
+    L, reps = 8, 3000
+    ids = [r * V + 3 for r in range(reps)]                       # all walkers start at node 3
+    leg = legacy.walks_generic(rp, col, w, L, ids, legacy.LegacyDraw(V, 11), consume_last=True)
+    nodes, lens = oracle.walks(rp, col, q, L, 11, 1, 3, reps * V, V)
+    phi = [list(map(int, r[:n])) for r, n in zip(nodes, lens)]
+    for pos in (1, 4, 6, 7):
+        a = np.bincount([x[pos] for x in leg if len(x) > pos], minlength=V).astype(np.float64)
+        b = np.bincount([x[pos] for x in phi if len(x) > pos], minlength=V).astype(np.float64)
+        m = (a + b) > 10
+        chi2 = (((a[m] - b[m]) ** 2) / (a[m] + b[m])).sum()
+        assert chi2 < stats.chi2.ppf(1 - 1e-4, int(m.sum()) - 1), (pos, chi2)
