@@ -29,6 +29,9 @@
 namespace g2v {
 
 constexpr int kWalkWarps = 8;   // warps per CTA
+#ifndef G2V_WALK_MINB
+#define G2V_WALK_MINB 8         // resident CTAs per SM the KC = 2 kernels are compiled for (32 registers)
+#endif
 
 __device__ __forceinline__ uint32_t hash_slot(int32_t c, int shift) {
     return ((uint32_t)c * 2654435761u) >> shift;
@@ -59,7 +62,7 @@ __device__ __forceinline__ uint32_t unvisited_weight(int hs, uint32_t mask, int 
 // KC = neighbour chunks (of TILE) kept in registers between the two passes: 2 for graphs whose rows
 // mostly fit 64 neighbours (fewer registers -> 8 resident CTAs per SM), 4 otherwise.
 template <bool BITMAP, int TILE, int KC>
-__global__ void __launch_bounds__(kWalkWarps * 32, KC == 2 ? 8 : 6)
+__global__ void __launch_bounds__(kWalkWarps * 32, KC == 2 ? G2V_WALK_MINB : 6)
 walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             const uint32_t *__restrict__ qw, int32_t V, int32_t L, int32_t Lpad, int32_t H,
             int32_t hshift, uint64_t seed, uint32_t group, int64_t walker_begin,
