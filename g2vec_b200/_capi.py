@@ -59,8 +59,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build.stale():
+    path = os.environ.get("G2VEC_B200_LIB") or _build.LIB     # A/B builds of the same ABI (profiles/variants)
+    if path == _build.LIB and _build.stale():
         try:
             _build.build_library()
         except Exception as exc:  # no nvcc, or compile error
