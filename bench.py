@@ -143,7 +143,20 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on stdout when the communicator is created; keep stdout for the one JSON
+        # line by pointing fd 1 at stderr while the group comes up (first collective included)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     assert world == args.gpus, "--gpus must equal WORLD_SIZE"
     import g2vec_b200 as g2v
     from g2vec_b200 import _capi, paths, cbow
