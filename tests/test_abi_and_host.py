@@ -139,3 +139,38 @@ def test_writers_formats(tmp_path):
     assert open(p + "_vectors.txt").read() == "GeneSymbol\tV0\tV1\nA1CF\t0.092807\t-0.044005\nAAK1\t1.500000\t2.250000\n"
     assert open(p + "_lgroups.txt").read() == "GeneSymbol\tLgroup(0:good,1:poor,2:other)\nA1CF\t1\nAAK1\t2\n"
     assert open(p + "_biomarkers.txt").read() == "GeneSymbol\nAAK1\n"
+
+
+def test_host_adjacency_on_all_ex_edges_matches_the_reference(golden_dir):
+    """graph.group_csr (vectorised host form of construct_adjMat, G2Vec.py:370-391) on all 216 540 ex_* edges
+    against the CSR the reference itself produced: same kept edges except on the 0.5 threshold, weights to 2e-6."""
+    from g2vec_b200 import graph
+    e = np.load(os.path.join(golden_dir, "ex_expr.npz"))
+    gr = np.load(os.path.join(golden_dir, "ex_graph.npz"))
+    for g in (0, 1):
+        rp, col, w = graph.group_csr(e["expr"], gr["label"], g, e["src"].astype(np.int32), e["dst"].astype(np.int32))
+        V = len(rp) - 1
+        got = dict(zip((np.repeat(np.arange(V, dtype=np.int64), np.diff(rp)) * V + col).tolist(), w.tolist()))
+        rrp, rcol, rw = gr["rowptr%d" % g], gr["col%d" % g], gr["w%d" % g]
+        ref = dict(zip((np.repeat(np.arange(V, dtype=np.int64), np.diff(rrp)) * V + rcol).tolist(), rw.tolist()))
+        both = set(got) & set(ref)
+        assert len(both) > 25000 and max(abs(got[k] - ref[k]) for k in both) < 2e-6
+        for k in set(got) ^ set(ref):
+            assert abs((got.get(k) or ref.get(k)) - 0.5) < 1e-5
+        assert len(set(got) ^ set(ref)) <= 2
+
+
+def test_cli_steps_1_and_2_reproduce_the_readme_counts(tmp_path):
+    """README.md:26-28 of the reference: n_samples 135, n_genes 7523, n_edges 216540 after the restriction."""
+    from g2vec_b200 import cli
+    from tests import helpers
+    ef, cf, nf, genes = helpers.write_ex_tsv(tmp_path)
+    data = cli.load_data(ef); clinical = cli.load_clinical(cf); network = cli.load_network(nf)
+    assert data["expr"].shape[0] == 135 and data["expr"].dtype == np.float32 and "NOT_IN_NETWORK" in data["gene"]
+    data["label"] = cli.match_labels(clinical, data["sample"])
+    data, network = cli.restrict(data, network)
+    assert data["expr"].shape == (135, 7523) and len(network["edge"]) == 216540
+    assert list(data["gene"]) == sorted(data["gene"]) and (data["gene"] == genes).all()
+    assert int((data["label"] == 0).sum()) == 77 and int((data["label"] == 1).sum()) == 58
+    with pytest.raises(SystemExit):
+        cli.match_labels({"nobody": 0}, data["sample"])
