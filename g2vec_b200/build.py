@@ -39,13 +39,30 @@ def stale():
 
 
 def build_library(force=False, verbose=False, extra=()):
+    """Compile into a temporary file and rename it over LIB while holding an exclusive file lock, so that the
+    ranks of a torchrun launch that all find the library stale neither compile into the same output nor dlopen
+    a half-written file: the first rank builds, the others wait on the lock and then find it fresh."""
+    import fcntl
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(ROOT, "include"), "-I", CSRC,
-                                                      "-o", LIB] + sources()
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not stale():          # another process built it while we waited
+                return LIB
+            tmp = "%s.tmp.%d" % (LIB, os.getpid())
+            cmd = [nvcc_path()] + NVCC_FLAGS + list(extra) + ["-I", os.path.join(ROOT, "include"), "-I", CSRC,
+                                                              "-o", tmp] + sources()
+            if verbose:
+                print(" ".join(cmd))
+            try:
+                subprocess.check_call(cmd)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

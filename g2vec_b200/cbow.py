@@ -44,11 +44,15 @@ def init_weights(n_genes, hidden, seed):
     return truncated_normal((n_genes, hidden), s, rng), truncated_normal((hidden,), s, rng)
 
 
-def shard_by_nnz(idx, lens, world, rank):
+def shard_by_nnz(idx, lens, world, rank, keep_order=False):
     """Deal window indices to ranks so every rank gets ~equal gather work: sort by length
-    (descending, stable) and deal round-robin."""
+    (descending, stable) and deal round-robin.  ``keep_order`` (mini-batches): deal the
+    shuffled list as it is, ``idx[rank::world]``, so that every batch stays a random sample of the list --
+    batch b of the N-GPU run is then the same set of windows as batch b of the 1-GPU run."""
     if world == 1:
         return idx
+    if keep_order:
+        return idx[rank::world]
     order = np.argsort(-lens[idx], kind="stable")
     return idx[order][rank::world]
 
@@ -317,7 +321,9 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
     model = CbowModel(win_rowptr, win_gene, labels, n_genes, hidden, W_ih0, W_ho0, optimizer, reduce, lr, algo=algo)
     lens = np.diff(rowptr_np).astype(np.int64)
     n_tr, n_va = len(tr), len(va)
-    tr_loc, va_loc = shard_by_nnz(np.asarray(tr), lens, world, rank), shard_by_nnz(np.asarray(va), lens, world, rank)
+    full_batch = batch <= 0 or batch >= n_tr
+    tr_loc = shard_by_nnz(np.asarray(tr), lens, world, rank, keep_order=not full_batch)
+    va_loc = shard_by_nnz(np.asarray(va), lens, world, rank)
     dev = model.device
     tr_d = torch.from_numpy(np.ascontiguousarray(tr_loc, dtype=np.int32)).to(dev)
     va_d = torch.from_numpy(np.ascontiguousarray(va_loc, dtype=np.int32)).to(dev)
@@ -331,7 +337,6 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
     result = model.W_ih.clone()
     hist, stop = [], None
     f32 = np.float32
-    full_batch = batch <= 0 or batch >= n_tr
     graph_ok = use_graph and dist is None and full_batch
     acc_pin = torch.zeros(4, dtype=torch.int64).pin_memory()
     steps = {}                               # with_train_eval -> CUDA-graph step (captured at first use)
@@ -370,7 +375,8 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
         # ACC[tr] of G2Vec.py:267 uses the post-update weights, i.e. exactly what the NEXT step's training
         # forward computes.  It is only printed every 5th step and at the stop, so the extra
         # forward pass is run only when its value is shown now; otherwise it arrives one step later for free.
-        show = ((step % 5 == 0 and log is not None) or step == max_epoch - 1 or eval_train == "always"
+        # (`show` must be the same on every rank -- the counters are all-reduced -- so it never looks at `log`)
+        show = (step % 5 == 0 or step == max_epoch - 1 or eval_train == "always"
                 or not full_batch)           # with mini-batches acc[1] mixes weights: always evaluate
         if graph_ok and step > 0:            # step 0 runs eagerly (and warms every kernel up before capture)
             if show not in steps:

@@ -214,7 +214,9 @@ def main(argv=None):
             pad[:r.shape[0]] = r
             parts = [torch.empty_like(pad) for _ in range(world)]
             dist.all_gather(parts, pad)
-            r = torch.unique(torch.cat([p[:int(c[0])] for p, c in zip(parts, cnts)], dim=0), dim=0)
+            # same content-determined row order as on one GPU (ascending key), so that --seed picks the same
+            # train/validation split whatever the number of GPUs
+            r = paths.canonical_rows(torch.cat([p[:int(c[0])] for p, c in zip(parts, cnts)], dim=0).contiguous())
         rows.append(r)
     prow, plab = paths.integrate(rows[0], rows[1])
     w_rowptr, w_gene, w_label = paths.windows_csr(prow, plab)
@@ -225,7 +227,7 @@ def main(argv=None):
 
     print(">>> 4. Compute distributed representations using modified CBOW")
     mat = cbow.train_cbow(w_rowptr, w_gene, w_label, n_genes, args.sizeHiddenlayer, args.learningRate,
-                          max_epoch=args.epoch, seed=args.seed, log=print if rank == 0 else None, algo=args.algo)
+                          max_epoch=args.epoch, seed=args.seed, log=print, algo=args.algo)   # print is silent off rank 0
     genes = data['gene']
     if rank != 0:
         dist.barrier()

@@ -14,8 +14,15 @@ records outputs of its own functions:
   ex_graph.npz     ex_* data through the reference's steps 1-3a: n_samples/n_genes/n_edges
                    (README.md:26-28), per-group CSR of construct_adjMat, and
                    generate_pathSet(adjMat, 80, 1) under np.random.seed(0) for group 0.
+  cbow_small.npz   the UNMODIFIED compute_genetovec (G2Vec.py:217-286) run on oracle/tf1_shim.py (the TF 1.x
+  cbow_ex.npz      ops it calls, restated on torch-CPU; TensorFlow itself is not installable here) under
+                   np.random.seed(seed): the dense pathList it was given (as CSR windows), the initial tensors
+                   tf.truncated_normal drew, the returned W_ih, every per-step ACC[val]/ACC[tr] the loop
+                   computed, the stop step and the printed log.  `python tests/golden/make_golden.py cbow`
+                   regenerates only these two.
 """
 import os
+import re
 import sys
 
 import numpy as np
@@ -27,6 +34,71 @@ from oracle.legacy import csr_from_dense  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 ref = ref_import.load()
+
+
+def run_reference_cbow(rowptr, gene, label, V, D, lr, seed):
+    """compute_genetovec(pathList, n_genes, hidden_size, learning_rate) exactly as main() calls it (G2Vec.py:74)
+    on the dense int32 pathList of integrate_pathSet (:310-322); np.random.seed(seed) fixes its shuffle (:219),
+    tf1_shim.seed_initialisers(seed) its two truncated_normal draws (:234-235)."""
+    import contextlib
+    import io
+    from oracle import tf1_shim
+    N = len(rowptr) - 1
+    P = np.zeros((N, V + 1), dtype=np.int32)
+    for n in range(N):
+        P[n, gene[rowptr[n]:rowptr[n + 1]]] = 1
+    P[:, -1] = label
+    tf1_shim.reset()
+    tf1_shim.seed_initialisers(seed)
+    np.random.seed(seed)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        W = ref.compute_genetovec(P, V, D, lr)
+    accs = [float(v) for k, v in tf1_shim.trace() if k == "eval"]       # val, tr, val, tr, ... (:266-267)
+    W0, Wo0 = tf1_shim.initial_values()
+    log = re.sub(r"\([0-9.]+ sec\)", "(T sec)", buf.getvalue())
+    return W, np.array(accs[0::2], dtype=np.float32), np.array(accs[1::2], dtype=np.float32), W0, Wo0.reshape(-1), log
+
+
+def learnable_windows(N, V, lmin, lmax, seed, noise):
+    """Small windows whose label is predictable from the genes (so the run trains for a while before it stops)."""
+    rs = np.random.RandomState(seed)
+    label = (rs.rand(N) < 0.5).astype(np.uint8)
+    lens = rs.randint(lmin, lmax + 1, size=N)
+    lens[:3] = 0                                  # empty windows (all-zero rows of the dense pathList)
+    rowptr = np.zeros(N + 1, dtype=np.int32)
+    rowptr[1:] = np.cumsum(lens)
+    genes, half = [], V // 2
+    for y, l in zip(label, lens):
+        p = np.full(V, noise / V)
+        lo = 0 if y == 0 else half
+        p[lo:lo + half] += (1 - noise) / half
+        genes.append(np.sort(rs.choice(V, size=l, replace=False, p=p / p.sum())))
+    return rowptr, np.concatenate(genes).astype(np.int32), label
+
+
+def save_cbow(name, rowptr, gene, label, V, D, lr, seed):
+    W, acc_val, acc_tr, W0, Wo0, log = run_reference_cbow(rowptr, gene, label, V, D, lr, seed)
+    touched = np.flatnonzero(np.abs(W - W0).max(axis=1) > 0)
+    stopped = "Epoch(stop)" in log
+    print(name, "windows", len(rowptr) - 1, "evaluated steps", len(acc_val), "stopped", stopped, "touched rows", len(touched))
+    print(log)
+    np.savez_compressed(os.path.join(OUT, name), rowptr=rowptr.astype(np.int32), gene=gene.astype(np.int16),
+                        label=label.astype(np.uint8), meta=np.array([V, D, seed], dtype=np.int64), lr=np.float64(lr),
+                        W_touched_rows=touched.astype(np.int32), W_touched=W[touched], acc_val=acc_val, acc_tr=acc_tr,
+                        # step whose validation accuracy dropped (loop index at the break, G2Vec.py:276-279); -1 = none
+                        stop_step=np.int64(len(acc_val) - 1 if stopped else -1), log=np.array(log),
+                        # the initial tensors are PCG64(seed) truncated normals (tests/helpers.pcg_init restates the
+                        # rule); W_ho and two float64 checksums of W_ih pin them without storing V*D floats
+                        W_ho0=Wo0, W_ih0_check=np.array([W0.astype(np.float64).sum(), np.abs(W0.astype(np.float64)).sum()]))
+
+
+def cbow_goldens():
+    rowptr, gene, label = learnable_windows(1500, 120, 1, 6, 5, 0.7)
+    save_cbow("cbow_small.npz", rowptr, gene, label, 120, 32, 0.005, 7)
+    from tests import helpers
+    (rowptr, gene, label), _ = helpers.ex_windows(reps=2)
+    save_cbow("cbow_ex.npz", rowptr, gene, label, 7523, 128, 0.005, 0)
 
 
 def pack_paths(ps):
@@ -136,4 +208,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["cbow"]:
+        cbow_goldens()
+    else:
+        main()
+        cbow_goldens()

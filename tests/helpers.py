@@ -88,3 +88,36 @@ def write_ex_tsv(tmp_path):
         f.writelines("%s\tNOT_IN_EXPRESSION\n" % g for g in genes[~seen])
         f.write("%s\tNOT_IN_EXPRESSION\n" % genes[0])
     return ef, cf, nf, genes
+
+
+def pcg_init(V, D, seed):
+    """The initial tensors of the CBOW goldens: what oracle/tf1_shim.truncated_normal draws for
+    tf.truncated_normal([V, D], stddev=1/sqrt(D)) then ([D, 1]) (G2Vec.py:234-235) after seed_initialisers(seed):
+    PCG64(seed) standard normals, re-drawn while |x| > 2, times stddev, float32."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = []
+    for shape in ((V, D), (D,)):
+        x = rng.standard_normal(size=shape)
+        bad = np.abs(x) > 2.0
+        while bad.any():
+            x[bad] = rng.standard_normal(size=int(bad.sum()))
+            bad = np.abs(x) > 2.0
+        out.append((x * (1.0 / np.sqrt(D))).astype(np.float32))
+    return out[0], out[1]
+
+
+def cbow_golden(name):
+    """tests/golden/cbow_*.npz -> dict with the windows, split, init and the reference's outputs."""
+    z = np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+    V, D, seed = (int(x) for x in z["meta"])
+    W0, Wo0 = pcg_init(V, D, seed)
+    assert (Wo0 == z["W_ho0"]).all()
+    chk = np.array([W0.astype(np.float64).sum(), np.abs(W0.astype(np.float64)).sum()])
+    assert np.allclose(chk, z["W_ih0_check"], rtol=0, atol=1e-9)
+    want = W0.copy()
+    want[z["W_touched_rows"]] = z["W_touched"]
+    N = len(z["rowptr"]) - 1
+    tr, va = oracle.split_indices(N, seed)
+    return {"rowptr": z["rowptr"], "gene": z["gene"].astype(np.int32), "label": z["label"], "V": V, "D": D, "seed": seed,
+            "lr": float(z["lr"]), "W0": W0, "Wo0": Wo0, "W_ref": want, "acc_val": z["acc_val"], "acc_tr": z["acc_tr"],
+            "stop_step": int(z["stop_step"]), "tr": tr, "va": va, "log": str(z["log"])}

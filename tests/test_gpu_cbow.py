@@ -48,8 +48,11 @@ def one_step(g2v, rowptr, gene, label, V, D, reduce="sum", optimizer="adam", see
 def test_one_step_gradients_and_adam(g2v, D):
     V, N = 500, 3000
     rowptr, gene, label = helpers.random_windows(N, V, 1, 80, seed=D)
-    rowptr[5] = rowptr[4]                                  # keep an empty window in the mix
-    rowptr, gene, label = helpers.random_windows(N, V, 1, 80, seed=D)
+    # keep empty windows in the mix (an all-zero row of the reference's dense pathList): window 4 gives its
+    # genes to window 5, the last window is emptied by dropping its genes
+    rowptr[5] = rowptr[4]
+    gene = gene[:rowptr[N - 1]].copy(); rowptr[N] = rowptr[N - 1]
+    assert rowptr[5] == rowptr[4] and rowptr[N] == rowptr[N - 1] and (np.diff(rowptr) >= 0).all()
     m, W0, Wo0, g_ih, g_ho, loss, nc = one_step(g2v, rowptr, gene, label, V, D)
     win = np.arange(N, dtype=np.int64)
     o_gih, o_gho, o_loss, o_nc = oracle.cbow_grad(rowptr, gene, label, win, N, W0, Wo0)
@@ -176,6 +179,41 @@ def test_ex_windows_early_stop_run(g2v):
     if stop == s_gpu:
         assert rel_max(got, want) < 5 * RTOL_VEC      # ~40 Adam steps of accumulated reassociation noise
     assert abs(hist[min(len(hist), len(info["history"])) - 1][1] - info["history"][min(len(hist), len(info["history"])) - 1][1]) < 5e-3
+
+
+@pytest.mark.parametrize("name", ["cbow_small.npz", "cbow_ex.npz"])
+@pytest.mark.parametrize("algo", ["rows", "rank1"])
+def test_gpu_equals_the_reference_run(g2v, name, algo):
+    """Against the reference ITSELF: tests/golden/cbow_*.npz hold what the unmodified compute_genetovec
+    (G2Vec.py:217-286, on oracle/tf1_shim.py) returned for these windows, this seed and these initial tensors.
+    The GPU run goes through the product's own split and init (same seed) and must give the reference's stop
+    step, accuracies (within 2 windows) and vectors (1e-4 relative, north_star)."""
+    g = helpers.cbow_golden(name)
+    from g2vec_b200 import cbow
+    W0, Wo0 = cbow.init_weights(g["V"], g["D"], g["seed"])
+    assert (W0 == g["W0"]).all() and (Wo0 == g["Wo0"]).all()      # product init == the tensors the reference drew
+    lines = []
+    got, info = g2v.train_cbow(g["rowptr"], g["gene"], g["label"], g["V"], g["D"], g["lr"], max_epoch=500,
+                               seed=g["seed"], log=lines.append, return_info=True, algo=algo)
+    assert info["stop_step"] == g["stop_step"], (info["stop_step"], g["stop_step"])
+    n_va, n_tr = len(g["va"]), len(g["tr"])
+    for (s, av, at), rv, rt in zip(info["history"], g["acc_val"], g["acc_tr"]):
+        assert abs(av - rv) <= 2.0 / n_va + 1e-7
+        assert at is None or abs(at - rt) <= 2.0 / n_tr + 1e-7
+    assert rel_max(got, g["W_ref"]) < RTOL_VEC
+    # same log lines as the reference printed (G2Vec.py:259,271,278,284): same epochs, same stop line; the
+    # four-decimal accuracies may differ by the window-flip tolerance above
+    import re
+    ref_lines = g["log"].splitlines()
+    assert len(lines) == len(ref_lines)
+    num = re.compile(r"ACC\[val\]=([0-9.]+)\tACC\[tr\]=([0-9.]+)")
+    for a, b in zip(lines, ref_lines):
+        assert a.split("ACC[val]")[0] == b.split("ACC[val]")[0]
+        ma, mb = num.search(a), num.search(b)
+        assert (ma is None) == (mb is None)
+        if ma:
+            assert abs(float(ma.group(1)) - float(mb.group(1))) <= 2.0 / n_va + 1.01e-4
+            assert abs(float(ma.group(2)) - float(mb.group(2))) <= 2.0 / n_tr + 1.01e-4
 
 
 def test_step_host_entry_point(g2v):
