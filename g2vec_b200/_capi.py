@@ -22,6 +22,10 @@ SIGNATURES = {
     "g2v_walk_workspace_bytes": (ctypes.c_size_t, []),
     "g2v_walk_launch": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _u64, _u32, _i64, _i64, _i64,
                                        _vp, _vp, _vp, _vp]),
+    "g2v_walk_packed_bytes": (ctypes.c_int, [_i32, _i64, _vp, _vp]),
+    "g2v_walk_prepare": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "g2v_walk_launch_packed": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _i32, _u64, _u32, _i64, _i64, _i64,
+                                              _vp, _vp, _vp, _vp, _vp]),
     "g2v_walk_host": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _u64, _u32, _i64, _i64, _i64, _vp, _vp]),
     "g2v_cbow_fwdbwd": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _i32, _i32, _i32, _vp]),
@@ -29,6 +33,12 @@ SIGNATURES = {
                                        _f32, _f32, _i32, _vp, _vp]),
     "g2v_cbow_adam_tick": (ctypes.c_int, [_vp, _f32, _f32, _f32, _vp]),
     "g2v_cbow_eval": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "g2v_cbow_slab_plan": (ctypes.c_int, [_i32, _i32, _vp]),
+    "g2v_cbow_slab_workspace_bytes": (ctypes.c_size_t, [_i64, _i32, _i32]),
+    "g2v_cbow_slab_setup": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "g2v_cbow_fwdbwd_slabs": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                             _i32, _i32, _i32, _i32, _vp, _vp]),
+    "g2v_cbow_eval_slabs": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "g2v_cbow_step_host": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                           _i32, _i32, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
     "g2v_cbow_r1_prepare": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),

@@ -129,6 +129,32 @@ class CbowModel:
         self._csc = (win.data_ptr(), int(w.shape[0]), cscptr.to(torch.int32), pos[order].to(torch.int32),
                      torch.empty(w.shape[0], dtype=torch.float32, device=self.device))
 
+    def prepare_slabs(self, win, win_begin=0, n_win=None):
+        """rows only, tables larger than the L2 (csrc/g2v_cbow_slab.cu): record once, for the static window list
+        ``win`` (int32 device tensor or None), where every window's sorted gene list crosses the gene-slab
+        boundaries; fwdbwd()/evaluate() over exactly this list then run slab by slab, L2-resident."""
+        if self.algo != "rows":
+            return False
+        import ctypes
+        if not hasattr(self, "_n_slabs"):
+            s = ctypes.c_int32(1)
+            _capi.check(self.lib.g2v_cbow_slab_plan(self.V, self.D, ctypes.byref(s)), "g2v_cbow_slab_plan")
+            self._n_slabs, self._slabs = int(s.value), {}
+        n = ((win.shape[0] if win is not None else self.rowptr.shape[0] - 1) - win_begin) if n_win is None else n_win
+        if self._n_slabs <= 1 or n <= 0:
+            return False
+        ws = torch.empty(int(self.lib.g2v_cbow_slab_workspace_bytes(int(n), self.D, self._n_slabs)), dtype=torch.uint8,
+                         device=self.device)
+        _capi.check(self.lib.g2v_cbow_slab_setup(self.rowptr.data_ptr(), self.gene.data_ptr(), self._ptr(win),
+                                                 int(win_begin), int(n), self.V, self._n_slabs, ws.data_ptr(),
+                                                 self._stream()), "g2v_cbow_slab_setup")
+        self._slabs[(self._ptr(win), int(win_begin), int(n))] = ws
+        return True
+
+    def _slab_ws(self, win, win_begin, n):
+        slabs = getattr(self, "_slabs", None)
+        return slabs.get((self._ptr(win), int(win_begin), int(n))) if slabs else None
+
     def grad_tensors(self):
         """What a multi-GPU step must all-reduce (sum) between fwdbwd() and update()."""
         return [self.g_ih, self.g_ho] if self.algo == "rows" else [self.c]
@@ -160,6 +186,15 @@ class CbowModel:
                                               self.s.data_ptr(), self.c.data_ptr(), self.acc.data_ptr(),
                                               self.acc.data_ptr() + 8, self.V, self.reduce, self._stream())
             _capi.check(rc, "g2v_cbow_r1_windows")
+            return
+        ws = self._slab_ws(win, win_begin, n)
+        if ws is not None:
+            rc = self.lib.g2v_cbow_fwdbwd_slabs(self.gene.data_ptr(), self.label.data_ptr(), self._ptr(win),
+                                                int(win_begin), int(n), 1.0 / float(n_total), self.W_ih.data_ptr(),
+                                                self.W_ho.data_ptr(), self.g_ih.data_ptr(), self.g_ho.data_ptr(),
+                                                self.acc.data_ptr(), self.acc.data_ptr() + 8, self.V, self.D,
+                                                self.reduce, self._n_slabs, ws.data_ptr(), self._stream())
+            _capi.check(rc, "g2v_cbow_fwdbwd_slabs")
             return
         rc = self.lib.g2v_cbow_fwdbwd(self.rowptr.data_ptr(), self.gene.data_ptr(), self.label.data_ptr(),
                                       self._ptr(win), int(win_begin), int(n), 1.0 / float(n_total),
@@ -197,6 +232,14 @@ class CbowModel:
                                               self._ptr(win), int(win_begin), int(n), 0.0, self.s.data_ptr(), 0, 0,
                                               self.acc.data_ptr() + 8 * slot, self.V, self.reduce, self._stream())
             _capi.check(rc, "g2v_cbow_r1_windows")
+            return
+        ws = self._slab_ws(win, win_begin, n)
+        if ws is not None:
+            rc = self.lib.g2v_cbow_eval_slabs(self.gene.data_ptr(), self.label.data_ptr(), self._ptr(win),
+                                              int(win_begin), int(n), self.W_ih.data_ptr(), self.W_ho.data_ptr(),
+                                              self.acc.data_ptr() + 8 * slot, self.V, self.D, self.reduce,
+                                              self._n_slabs, ws.data_ptr(), self._stream())
+            _capi.check(rc, "g2v_cbow_eval_slabs")
             return
         rc = self.lib.g2v_cbow_eval(self.rowptr.data_ptr(), self.gene.data_ptr(), self.label.data_ptr(),
                                     self._ptr(win), int(win_begin), int(n), self.W_ih.data_ptr(),
@@ -330,6 +373,9 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
 
     if algo == "rank1" and (batch <= 0 or batch >= n_tr) and len(tr_loc):
         model.prepare_csc(tr_d)
+    if algo == "rows" and full_batch:            # tables larger than the L2: gene-slab passes over the static lists
+        model.prepare_slabs(tr_d)
+        model.prepare_slabs(va_d)
     if log:
         log("     Start training the modified CBOW with early stopping")
     t0 = time.time()

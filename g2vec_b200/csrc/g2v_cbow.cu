@@ -22,30 +22,12 @@
 // contraction.  Algorithmic bytes per window: l*(8D+4)+5, per step + 32*V*D (Adam).
 #include <stdlib.h>
 
-#include "g2v_common.cuh"
+#include "g2v_cbow_common.cuh"
 
 namespace g2v {
 
-constexpr int kCbowWarps = 8;
 constexpr bool kDefaultGatherTma = false;
 constexpr bool kDefaultScatterTma = false;   // see profiles/README.md for the measurement behind this choice
-
-__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
-__device__ __forceinline__ void red_add4(float *p, float4 v) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
-                 "f"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ float sigmoid_stable(float x) {
-    if (x >= 0.f) { const float z = expf(-x); return 1.f / (1.f + z); }
-    const float z = expf(x);
-    return z / (1.f + z);
-}
-
-struct CtaAcc {   // per-CTA accumulators in shared memory
-    double loss;
-    unsigned long long correct;
-};
 
 // SCATTER_TMA: the gradient row dO*W_ho (identical for every gene of the window) is staged once in
 // shared memory and added into g_ih[gene,:] with one TMA bulk reduction per gene
@@ -365,7 +347,7 @@ cbow_update_kernel(float *__restrict__ W, float *__restrict__ M, float *__restri
     }
 }
 
-static int rows_grid(const void *kernel, size_t smem, int64_t n_win, int *grid_out) {
+int rows_grid(const void *kernel, size_t smem, int64_t n_win, int *grid_out) {
     DeviceProps dp;
     if (device_props(&dp)) return 1;
     if (dp.cc_major != 10) { set_error("needs an sm_100 device (found sm_%d%d); no CPU fallback", dp.cc_major, dp.cc_minor); return 2; }

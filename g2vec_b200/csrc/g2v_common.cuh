@@ -68,6 +68,23 @@ __host__ __device__ __forceinline__ uint64_t draw64(uint64_t seed, uint64_t subs
     return (s & 1u) ? (((uint64_t)w[3] << 32) | w[2]) : (((uint64_t)w[1] << 32) | w[0]);
 }
 
+// ---- canonical path rows (G2Vec.py:345 tuple(sorted(path))): padding value and the 64-bit row key ------
+// key = finish(sum over sorted positions i of term(node_i, i)); equal rows have equal keys, the converse is
+// never assumed (g2v_paths.cu compares rows in full).
+constexpr int32_t kPathPad = 0x7fffffff;
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {      // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+__host__ __device__ __forceinline__ uint64_t path_key_term(int32_t v, int i) {
+    return mix64(((uint64_t)(uint32_t)v << 20) ^ (uint64_t)(i + 1) * 0x9e3779b97f4a7c15ull);
+}
+__host__ __device__ __forceinline__ uint64_t path_key_finish(uint64_t h) {
+    return mix64(h) >> 1;                                              // 63 bits: non-negative as int64
+}
+
 // ---- warp helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -80,11 +97,13 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 __device__ __forceinline__ uint32_t warp_inclusive_scan_u32(uint32_t v, int lane) {
+    (void)lane;
+    // shfl.up's own predicate output says whether the source lane exists: SHFL.UP P, ... ; @P IADD -- two
+    // instructions per stage instead of shuffle + compare + select + add
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-    }
+    for (int o = 1; o < 32; o <<= 1)
+        asm volatile("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff; @p add.u32 %0, %0, t; }"
+                     : "+r"(v) : "r"(o));
     return v;
 }
 

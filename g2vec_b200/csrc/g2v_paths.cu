@@ -19,14 +19,7 @@
 namespace g2v {
 
 constexpr int kPathWarps = 8;
-constexpr int32_t kPad = 0x7fffffff;
-
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {      // splitmix64 finaliser
-    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
-    x ^= x >> 27; x *= 0x94d049bb133111ebull;
-    x ^= x >> 31;
-    return x;
-}
+constexpr int32_t kPad = kPathPad;
 
 __global__ void __launch_bounds__(kPathWarps * 32)
 paths_canon_kernel(const int32_t *__restrict__ nodes, int64_t n, int32_t L, int32_t P,
@@ -56,10 +49,10 @@ paths_canon_kernel(const int32_t *__restrict__ nodes, int64_t n, int32_t L, int3
         for (int i = lane; i < L; i += 32) {
             const int32_t v = s[i];
             sorted[(size_t)r * L + i] = v;
-            if (v != kPad) h += mix64(((uint64_t)(uint32_t)v << 20) ^ (uint64_t)(i + 1) * 0x9e3779b97f4a7c15ull);
+            if (v != kPad) h += path_key_term(v, i);
         }
         h = warp_sum_u64(h);
-        if (lane == 0) key[r] = mix64(h) >> 1;                        // 63 bits: stays non-negative as int64
+        if (lane == 0) key[r] = path_key_finish(h);
         __syncwarp();
     }
 }

@@ -6,32 +6,44 @@
 //     prob = adjMat[cur]; prob[path] = 0                  -> CSR row, visited test per neighbour
 //     if prob.sum() > 0: cur = choice(p = prob / sum)     -> integer inverse CDF, one Philox draw
 //     else: break
+// and at the end `path = tuple(sorted(path))` (:345) -- optionally fused here (CANON): the path is already
+// in shared memory, so the warp sorts it there (bitonic), writes the sorted row and its 64-bit key, and the
+// separate canonicalise launch with its re-read of the rows disappears.
 //
-// Layout: the group's graph as CSR in HBM (rowptr int32 [V+1], col int32 [E] ascending per
-// row, qw uint32 [E]); both are read with coalesced 128 B warp loads (32 neighbours per
-// request).  Per warp in shared memory: the path (L ints, written back once, coalesced) and
-// the visited set -- a V-bit bitmap (one LDS per neighbour) while 8 warps' bitmaps fit in 56 KB
-// (V <= ~46k at L = 80), otherwise an open-addressing hash set of >= 3L slots whose size is
-// independent of V (200k-node graphs keep full occupancy).  KC (2 or 4) neighbour chunks are kept in
-// registers between the two passes (per-chunk totals with REDUX.SUM, then one scan inside the selected
-// chunk); rows longer than 32*KC neighbours re-read the tail (L1/L2 hits).  Philox draws are evaluated
-// 32 steps at a time, one step per lane.
-// Walkers are handed out by an atomic ticket so that warps whose walker dead-ends early
-// (62 % of ex_* start nodes have no out-edge) immediately take the next one.
+// Graph layouts in HBM (template LAYOUT):
+//   LAY_CSR  rowptr int32 [V+1], col int32 [E], qw uint32 [E]          -- the plain C-ABI arrays (g2v_walk_launch)
+//   LAY_E8   rows int2 {begin,end} [V], edges uint2 {col, qw} [E]      -- one LDG.64 per neighbour
+//   LAY_E4   rows int2 [V], edges uint32 = col | (qw-32768) << 16 [E]  -- V <= 65536 and 32768 <= qw <= 65536
+//            (the |PCC| in [0.5, 1] range of the reference's edges, G2Vec.py:389): one LDG.64 brings TWO
+//            neighbours per lane, 64 per warp request
+// g2v_walk_prepare packs the CSR once per graph (the graph is static across all repetitions).
 //
-// Integer arithmetic only on the selection path => bit-exact against oracle/g2v_oracle.c for
-// any scan order:  T = sum of unvisited qw (uint64), r = mulhi64(x, T), first inclusive
-// prefix > r.
+// Per warp in shared memory: the path (written back once, coalesced) and the visited set -- a V-bit bitmap
+// (one LDS per neighbour) while 8 warps' bitmaps fit in 56 KB, otherwise an open-addressing hash set of
+// >= 3L slots whose size is independent of V (200k-node graphs keep full occupancy).
+// Rows of at most one chunk (32 or 64 neighbours) take the short path: load, visited test, ONE warp scan that
+// yields both the total and the prefix sums, draw, ballot.  Longer rows keep KC chunks in registers between the
+// two passes (per-chunk totals with REDUX.SUM, then one scan inside the selected chunk) and re-read the tail.
+// Philox draws are evaluated 32 steps at a time, one step per lane.  Walkers are handed out by an atomic
+// ticket so that warps whose walker dead-ends early (62 % of ex_* start nodes have no out-edge) immediately
+// take the next one.
+//
+// Integer arithmetic only on the selection path => bit-exact against oracle/g2v_oracle.c for any scan
+// order:  T = sum of unvisited qw (uint64), r = mulhi64(x, T), first inclusive prefix > r.
 #include <stdlib.h>
+#include <string.h>
 
 #include "g2v_common.cuh"
 
 namespace g2v {
 
 constexpr int kWalkWarps = 8;   // warps per CTA
+constexpr int kKC = 2;          // neighbour chunks kept in registers on the long-row path
 #ifndef G2V_WALK_MINB
-#define G2V_WALK_MINB 6         // resident CTAs per SM the KC = 2 kernels are compiled for (measured: 8 -> 2.73 ms, 6 -> 2.65 ms)
+#define G2V_WALK_MINB 6         // resident CTAs per SM the kernels are compiled for (register cap 40)
 #endif
+
+enum { LAY_CSR = 0, LAY_E8 = 1, LAY_E4 = 2 };
 
 __device__ __forceinline__ uint32_t hash_slot(int32_t c, int shift) {
     return ((uint32_t)c * 2654435761u) >> shift;
@@ -55,200 +67,318 @@ __device__ __forceinline__ uint32_t unvisited_weight(int hs, uint32_t mask, int 
     }
 }
 
-// One TILE of lanes (8, 16 or 32) per walker, 32/TILE walkers per warp.  The loop is a flat state
-// machine -- every iteration is "one step for every tile of the warp" -- so that tiles whose walkers end
-// at different times stay converged: finishing a walk (row write-out, visited-set reset) and fetching
-// the next ticket are short predicated sections of the same iteration.
-// KC = neighbour chunks (of TILE) kept in registers between the two passes: 2 for graphs whose rows
-// mostly fit 64 neighbours (fewer registers -> 8 resident CTAs per SM), 4 otherwise.
-template <bool BITMAP, int TILE, int KC>
-__global__ void __launch_bounds__(kWalkWarps * 32, KC == 2 ? G2V_WALK_MINB : 6)
-walk_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-            const uint32_t *__restrict__ qw, int32_t V, int32_t L, int32_t Lpad, int32_t H,
-            int32_t hshift, uint64_t seed, uint32_t group, int64_t walker_begin,
-            int64_t n_walkers, int64_t walker_stride, int32_t *__restrict__ out_nodes,
-            int32_t *__restrict__ out_len, unsigned long long *__restrict__ ticket) {
+struct WalkGraphPtrs {
+    const int32_t *rows;    // LAY_CSR: rowptr [V+1];  else int2 {begin, end} [V]
+    const void *edges;      // LAY_CSR: col [E];  LAY_E8: uint2 [E];  LAY_E4: uint32 [E] (+1 pad)
+    const uint32_t *qw;     // LAY_CSR only
+};
+
+// One chunk of a row: lane's neighbours jb + lane*EPL + {0 .. EPL-1}, masked weights (0 = outside [b, e) or
+// already visited) and node ids.  LAY_E4: jb is even (the caller aligns the first chunk down), so the pair
+// is one aligned 8-byte load; the element in front of an odd `b` and the one at `e` are masked out.
+template <int LAYOUT, bool BITMAP>
+__device__ __forceinline__ void load_chunk(const WalkGraphPtrs &g, int32_t jb, int32_t b, int32_t e, int lane, int hs,
+                                           uint32_t hmask, int hshift, int32_t &c0, int32_t &c1, uint32_t &q0,
+                                           uint32_t &q1) {
+    if (LAYOUT == LAY_E4) {
+        const int32_t j = jb + 2 * lane;
+        uint2 w = make_uint2(0u, 0u);
+        if (j < e) w = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint32_t *>(g.edges) + j));
+        c0 = (int32_t)(w.x & 0xffffu); c1 = (int32_t)(w.y & 0xffffu);
+        const uint32_t a0 = (j >= b && j < e) ? (w.x >> 16) + 32768u : 0u;
+        const uint32_t a1 = (j + 1 < e) ? (w.y >> 16) + 32768u : 0u;           // j + 1 >= b always
+        q0 = unvisited_weight<BITMAP>(hs, hmask, hshift, c0, a0);
+        q1 = unvisited_weight<BITMAP>(hs, hmask, hshift, c1, a1);
+    } else {
+        const int32_t j = jb + lane;
+        uint32_t a0 = 0u;
+        c0 = 0;
+        if (LAYOUT == LAY_E8) {
+            uint2 w = make_uint2(0u, 0u);
+            if (j < e) w = __ldg(reinterpret_cast<const uint2 *>(g.edges) + j);
+            c0 = (int32_t)w.x; a0 = w.y;
+        } else if (j < e) {
+            c0 = __ldg(reinterpret_cast<const int32_t *>(g.edges) + j);
+            a0 = __ldg(g.qw + j);
+        }
+        q0 = unvisited_weight<BITMAP>(hs, hmask, hshift, c0, a0);
+        c1 = 0; q1 = 0u;
+    }
+}
+
+// Inclusive warp scan of p; the first lane whose prefix exceeds `rem` holds the chosen neighbour.
+template <int EPL>
+__device__ __forceinline__ int32_t pick_in_chunk(uint32_t p, uint32_t q0, int32_t c0, int32_t c1, uint32_t incl,
+                                                 uint32_t rem) {
+    const unsigned hit = __ballot_sync(0xffffffffu, incl > rem);
+    const int32_t sel = (EPL == 2 && !(incl - p + q0 > rem)) ? c1 : c0;
+    return __shfl_sync(0xffffffffu, sel, __ffs(hit) - 1);
+}
+
+template <bool BITMAP, int LAYOUT, bool CANON>
+__global__ void __launch_bounds__(kWalkWarps * 32, G2V_WALK_MINB)
+walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H, int32_t hshift, uint64_t seed,
+            uint32_t group, int64_t walker_begin, int64_t n_walkers, int64_t walker_stride,
+            int32_t *__restrict__ out_nodes, int32_t *__restrict__ out_len, unsigned long long *__restrict__ out_key,
+            unsigned long long *__restrict__ ticket) {
     int32_t *const smem = g2v_walk_smem;
-    constexpr int NT = 32 / TILE;
+    constexpr int EPL = LAYOUT == LAY_E4 ? 2 : 1;       // neighbours per lane per chunk
+    constexpr int CH = 32 * EPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile = lane / TILE, tl = lane % TILE, tbase = tile * TILE;
-    const unsigned tmask = TILE == 32 ? 0xffffffffu : (((1u << TILE) - 1u) << tbase);
-    const int path = (warp * NT + tile) * (Lpad + H);   // offsets into smem (ints), not pointers
+    const int path = warp * (Lpad + H);                  // offsets into smem (ints), not pointers
     const int hs = path + Lpad;
     const uint32_t hmask = (uint32_t)H - 1u;
 
-    for (int i = tl; i < H; i += TILE) smem[hs + i] = BITMAP ? 0 : -1;
-    __syncwarp(tmask);
-
-    bool have = false, done = false, dirty = false;
-    unsigned long long t = 0;
-    uint64_t subseq = 0;
-    int32_t cur = 0, n = 0, s = 0, dbase = -1;
-    uint32_t dlo = 0, dhi = 0;                           // lane tl holds the draw of step dbase + tl
+    for (int i = lane; i < H; i += 32) smem[hs + i] = BITMAP ? 0 : -1;
+    __syncwarp();
 
     while (true) {
-        if (!have && !done) {                            // take the next walker
-            unsigned long long tk = 0;
-            if (tl == 0) tk = atomicAdd(ticket, 1ull);
-            tk = __shfl_sync(tmask, tk, tbase);
-            if ((int64_t)tk >= n_walkers) {
-                done = true;
-            } else {
-                t = tk;
-                const int64_t w = walker_begin + (int64_t)tk * walker_stride;
-                subseq = ((uint64_t)group << 40) + (uint64_t)w;
-                cur = (int32_t)(w % V);
-                n = 0; s = 0; dbase = -1; dirty = false; have = true;
-            }
-        }
-        if (TILE == 32) {
-            if (done) break;                             // one walker per warp: nothing to wait for
-        } else {
-            if (__all_sync(0xffffffffu, done)) break;
-            if (!have) continue;
-        }
+        // ------------------------------------------------------------------ take the next walker
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1ull);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((int64_t)t >= n_walkers) break;
+        const int64_t w = walker_begin + (int64_t)t * walker_stride;
+        const uint64_t subseq = ((uint64_t)group << 40) + (uint64_t)w;
+        int32_t cur = (int32_t)(w % V);
+        int32_t n = 0;                                   // nodes appended = step index + 1
+        uint32_t dlo = 0, dhi = 0;                       // lane holds the draw of step (s & ~31) + lane
+        bool dirty = false;
 
-        // ---------------------------------------------------------------- one step of this tile's walker
-        smem[path + n] = cur;                            // every lane of the tile stores the same value
-        ++n;
-        bool end = (s == L - 1);                         // the L-th node is appended, never expanded
-        int32_t b = 0, e = 0;
-        if (!end) {
-            b = __ldg(rowptr + cur); e = __ldg(rowptr + cur + 1);
-            end = (b == e);                              // no out-edges: dead end
-        }
-        if (!end) {
-            if (BITMAP) {                                // visited.insert(cur), uniform across the tile
-                const int32_t wv = smem[hs + (cur >> 5)];
-                __syncwarp(tmask);
-                smem[hs + (cur >> 5)] = wv | (1 << (cur & 31));
+        while (true) {
+            // every lane stores the same value: each lane later reads only what it wrote itself
+            smem[path + n] = cur;
+            const int32_t s = n++;
+            if (s == L - 1) break;                       // the L-th node is appended, never expanded
+            int32_t b, e;
+            if (LAYOUT == LAY_CSR) {
+                b = __ldg(g.rows + cur); e = __ldg(g.rows + cur + 1);
+            } else {
+                const int2 be = __ldg(reinterpret_cast<const int2 *>(g.rows) + cur);
+                b = be.x; e = be.y;
+            }
+            if (b == e) break;                           // no out-edges: dead end
+            if (BITMAP) {                                // visited.insert(cur): same word, same value in every lane
+                smem[hs + (cur >> 5)] |= (1 << (cur & 31));
             } else {
                 uint32_t i = hash_slot(cur, hshift);
                 while (smem[hs + i] >= 0) i = (i + 1) & hmask;
-                __syncwarp(tmask);
+                __syncwarp();                            // every lane has found the free slot before any lane fills it
                 smem[hs + i] = cur;
             }
             dirty = true;
-            __syncwarp(tmask);
+            if ((s & 31) == 0) {                         // 32 steps of 64-bit Philox draws at once, one per lane
+                const uint64_t d = draw64(seed, subseq, (uint32_t)(s + lane));
+                dlo = (uint32_t)d; dhi = (uint32_t)(d >> 32);
+            }
+            const uint32_t xlo = __shfl_sync(0xffffffffu, dlo, s & 31), xhi = __shfl_sync(0xffffffffu, dhi, s & 31);
 
-            // ---- pass 1: weight of the unvisited out-neighbours, per chunk of TILE (REDUX.SUM)
-            uint32_t mq[KC], tot[KC];
-            int32_t mc[KC];
-            unsigned long long T = 0;
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                mq[k] = 0; mc[k] = -1; tot[k] = 0;
-                if (k == 0 || b + k * TILE < e) {        // tile-uniform (chunk 0 always exists: b < e)
-                    const int32_t j = b + k * TILE + tl;
-                    const bool in = j < e;
-                    const int32_t c = in ? __ldg(col + j) : 0;       // predicated loads, no branch
-                    const uint32_t q = in ? __ldg(qw + j) : 0u;
-                    mc[k] = c;
-                    mq[k] = unvisited_weight<BITMAP>(hs, hmask, hshift, c, q);
-                    tot[k] = __reduce_add_sync(tmask, mq[k]);         // <= 32 * 2^24
-                    T += tot[k];
-                }
-            }
-            for (int32_t jb = b + KC * TILE; jb < e; jb += TILE) {   // rows longer than KC*TILE neighbours
-                const int32_t j = jb + tl;
-                uint32_t q = 0;
-                if (j < e) q = unvisited_weight<BITMAP>(hs, hmask, hshift, __ldg(col + j), __ldg(qw + j));
-                T += __reduce_add_sync(tmask, q);
-            }
-            const bool has_tail = b + KC * TILE < e;
-            if (T == 0) {
-                end = true;                              // every neighbour already visited
+            const int32_t jb0 = EPL == 2 ? (b & ~1) : b;
+            int32_t nxt;
+            if (e - jb0 <= CH) {
+                // ---- short row: one chunk.  One scan gives the total (lane 31) and the prefix sums.
+                int32_t c0, c1; uint32_t q0, q1;
+                load_chunk<LAYOUT, BITMAP>(g, jb0, b, e, lane, hs, hmask, hshift, c0, c1, q0, q1);
+                const uint32_t p = q0 + q1;
+                const uint32_t incl = warp_inclusive_scan_u32(p, lane);
+                const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);            // <= 64 * 2^24 < 2^32
+                if (T == 0) break;                       // every neighbour already visited
+                // r = floor(x*T / 2^64) with T < 2^32: two 32x32 multiplies instead of a 64x64 high multiply
+                const unsigned long long lo = (unsigned long long)xlo * T;
+                const uint32_t rem = (uint32_t)(((unsigned long long)xhi * T + (lo >> 32)) >> 32);
+                nxt = pick_in_chunk<EPL>(p, q0, c0, c1, incl, rem);
             } else {
-                // ---- one 64-bit Philox draw per step, r uniform in [0, T); TILE steps are drawn at once,
-                //      one per lane (counter-based: lane tl evaluates step dbase + tl)
-                if ((s / TILE) * TILE != dbase) {
-                    dbase = (s / TILE) * TILE;
-                    const uint64_t d = draw64(seed, subseq, (uint32_t)(dbase + tl));
-                    dlo = (uint32_t)d; dhi = (uint32_t)(d >> 32);
+                // ---- long row: pass 1 = per-chunk totals (first kKC chunks stay in registers), pass 2 = select
+                uint32_t P[kKC], Q0[kKC], tot[kKC];
+                int32_t C0[kKC], C1[kKC];
+                unsigned long long T = 0;
+#pragma unroll
+                for (int k = 0; k < kKC; ++k) {
+                    P[k] = 0; Q0[k] = 0; tot[k] = 0; C0[k] = 0; C1[k] = 0;
+                    if (jb0 + k * CH < e) {              // warp-uniform
+                        uint32_t q1;
+                        load_chunk<LAYOUT, BITMAP>(g, jb0 + k * CH, b, e, lane, hs, hmask, hshift, C0[k], C1[k], Q0[k], q1);
+                        P[k] = Q0[k] + q1;
+                        tot[k] = __reduce_add_sync(0xffffffffu, P[k]);
+                        T += tot[k];
+                    }
                 }
-                const int src = tbase + (s % TILE);
-                const uint64_t x = ((uint64_t)__shfl_sync(tmask, dhi, src) << 32) | __shfl_sync(tmask, dlo, src);
-                // r = floor(x*T / 2^64).  Without a tail T < 2^32 (KC chunk totals of at most 2^29), so the
-                // product needs two 32x32 multiplies instead of a 64x64 high multiply.
-                unsigned long long rem;                  // r - (weight of the chunks already skipped)
-                if (!has_tail) {
-                    const uint32_t T32 = (uint32_t)T;
-                    const unsigned long long lo = (unsigned long long)(uint32_t)x * T32;
-                    rem = ((unsigned long long)(uint32_t)(x >> 32) * T32 + (lo >> 32)) >> 32;
-                } else {
-                    rem = __umul64hi(x, T);
+                for (int32_t jb = jb0 + kKC * CH; jb < e; jb += CH) {
+                    int32_t c0, c1; uint32_t q0, q1;
+                    load_chunk<LAYOUT, BITMAP>(g, jb, b, e, lane, hs, hmask, hshift, c0, c1, q0, q1);
+                    T += __reduce_add_sync(0xffffffffu, q0 + q1);
                 }
-
-                // ---- pass 2: chunk that contains r (tile-uniform scalar search), then one scan inside it
-                int32_t nxt = -1;
+                if (T == 0) break;
+                unsigned long long rem = __umul64hi(((unsigned long long)xhi << 32) | xlo, T);
+                nxt = -1;
                 bool found = false;
 #pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    if (!found && (k == 0 || b + k * TILE < e)) {
+                for (int k = 0; k < kKC; ++k) {
+                    if (!found && jb0 + k * CH < e) {
                         if (rem < (unsigned long long)tot[k]) {
-                            uint32_t incl = mq[k];
-#pragma unroll
-                            for (int o = 1; o < TILE; o <<= 1) {
-                                const uint32_t up = __shfl_up_sync(tmask, incl, o, TILE);
-                                if (tl >= o) incl += up;
-                            }
-                            const unsigned hit = __ballot_sync(tmask, incl > (uint32_t)rem);
-                            nxt = __shfl_sync(tmask, mc[k], __ffs(hit) - 1);
+                            const uint32_t incl = warp_inclusive_scan_u32(P[k], lane);
+                            nxt = pick_in_chunk<EPL>(P[k], Q0[k], C0[k], C1[k], incl, (uint32_t)rem);
                             found = true;
                         } else {
                             rem -= tot[k];
                         }
                     }
                 }
-                for (int32_t jb = b + KC * TILE; !found && jb < e; jb += TILE) {
-                    const int32_t j = jb + tl;
-                    int32_t c = -1;
-                    uint32_t q = 0;
-                    if (j < e) {
-                        c = __ldg(col + j);
-                        q = unvisited_weight<BITMAP>(hs, hmask, hshift, c, __ldg(qw + j));
-                    }
-                    const uint32_t ct = __reduce_add_sync(tmask, q);
+                for (int32_t jb = jb0 + kKC * CH; !found && jb < e; jb += CH) {
+                    int32_t c0, c1; uint32_t q0, q1;
+                    load_chunk<LAYOUT, BITMAP>(g, jb, b, e, lane, hs, hmask, hshift, c0, c1, q0, q1);
+                    const uint32_t p = q0 + q1;
+                    const uint32_t ct = __reduce_add_sync(0xffffffffu, p);
                     if (rem < (unsigned long long)ct) {
-                        uint32_t incl = q;
-#pragma unroll
-                        for (int o = 1; o < TILE; o <<= 1) {
-                            const uint32_t up = __shfl_up_sync(tmask, incl, o, TILE);
-                            if (tl >= o) incl += up;
-                        }
-                        const unsigned hit = __ballot_sync(tmask, incl > (uint32_t)rem);
-                        nxt = __shfl_sync(tmask, c, __ffs(hit) - 1);
+                        const uint32_t incl = warp_inclusive_scan_u32(p, lane);
+                        nxt = pick_in_chunk<EPL>(p, q0, c0, c1, incl, (uint32_t)rem);
                         found = true;
                     } else {
                         rem -= ct;
                     }
                 }
-                cur = nxt;
-                ++s;
+            }
+            cur = nxt;
+        }
+
+        // ---------------------------------------------------------------- walk finished: n nodes in smem
+        int32_t *row = out_nodes + (size_t)t * (size_t)L;
+        if (!CANON) {
+            for (int i = lane; i < L; i += 32) row[i] = (i < n) ? smem[path + i] : -1;     // visit order
+        } else {
+            // tuple(sorted(path)) (G2Vec.py:345): bitonic network over the next power of two, INT32_MAX padding
+            int P2 = 1;
+            while (P2 < n) P2 <<= 1;
+            if (n > 1) {
+                for (int i = n + lane; i < P2; i += 32) smem[path + i] = kPathPad;
+                __syncwarp();
+                for (int k = 2; k <= P2; k <<= 1)
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        for (int x = lane; x < (P2 >> 1); x += 32) {
+                            const int i = ((x / j) * 2 * j) + (x % j), l = i + j;
+                            const bool up = (i & k) == 0;
+                            const int32_t a = smem[path + i], c = smem[path + l];
+                            if ((a > c) == up) { smem[path + i] = c; smem[path + l] = a; }
+                        }
+                        __syncwarp();
+                    }
+            }
+            uint64_t h = 0;
+            for (int i = lane; i < L; i += 32) {
+                const int32_t v = (i < n) ? smem[path + i] : kPathPad;
+                row[i] = v;
+                if (i < n) h += path_key_term(v, i);
+            }
+            h = warp_sum_u64(h);
+            if (lane == 0) out_key[t] = path_key_finish(h);
+        }
+        if (lane == 0) out_len[t] = n;
+        if (dirty) {
+            if (BITMAP) {
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) smem[hs + (smem[path + i] >> 5)] = 0;   // only the touched words
+            } else {
+                for (int i = lane; i < H; i += 32) smem[hs + i] = -1;
             }
         }
-        if (end) {                                       // walk finished: write the row once, coalesced
-            __syncwarp(tmask);
-            int32_t *row = out_nodes + (size_t)t * (size_t)L;
-            for (int i = tl; i < L; i += TILE) row[i] = (i < n) ? smem[path + i] : -1;
-            if (tl == 0) out_len[t] = n;
-            if (dirty) {
-                __syncwarp(tmask);
-                if (BITMAP) {
-                    for (int i = tl; i < n; i += TILE) smem[hs + (smem[path + i] >> 5)] = 0;   // only the touched words
-                } else {
-                    for (int i = tl; i < H; i += TILE) smem[hs + i] = -1;
-                }
-            }
-            __syncwarp(tmask);
-            have = false;
-        }
+        __syncwarp();
+    }
+}
+
+// ---- graph packing (once per graph) -------------------------------------------------------------
+__global__ void walk_range_kernel(const uint32_t *__restrict__ qw, int64_t E, int32_t *__restrict__ flag) {
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t q = __ldg(qw + i);
+        bad = bad || q < 32768u || q > 65536u;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+__global__ void walk_pack_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                 const uint32_t *__restrict__ qw, int32_t V, int64_t E, int32_t layout,
+                                 int2 *__restrict__ rows, void *__restrict__ edges) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = tid; v < V; v += nth) rows[v] = make_int2(__ldg(rowptr + v), __ldg(rowptr + v + 1));
+    if (layout == LAY_E8) {
+        uint2 *e8 = reinterpret_cast<uint2 *>(edges);
+        for (int64_t j = tid; j < E; j += nth) e8[j] = make_uint2((uint32_t)__ldg(col + j), __ldg(qw + j));
+    } else {
+        uint32_t *e4 = reinterpret_cast<uint32_t *>(edges);
+        for (int64_t j = tid; j < E + 2; j += nth)                       // two pad words: the pair load at E-1
+            e4[j] = j < E ? ((uint32_t)__ldg(col + j) | ((__ldg(qw + j) - 32768u) << 16)) : 0u;
     }
 }
 
 __global__ void test_draws_kernel(uint64_t seed, uint64_t subseq, int32_t n, uint64_t *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = draw64(seed, subseq, (uint32_t)i);
+}
+
+typedef void (*walk_kern_t)(const WalkGraphPtrs, int32_t, int32_t, int32_t, int32_t, int32_t, uint64_t, uint32_t,
+                            int64_t, int64_t, int64_t, int32_t *, int32_t *, unsigned long long *,
+                            unsigned long long *);
+
+static int launch_walk(const WalkGraphPtrs &g, int layout, int32_t V, int64_t E, int32_t L, uint64_t seed,
+                       uint32_t group, int64_t walker_begin, int64_t walker_end, int64_t walker_stride,
+                       int32_t *out_nodes, int32_t *out_len, int64_t *out_key, void *workspace, cudaStream_t st,
+                       const char *who) {
+    G2V_REQUIRE(V > 0 && E >= 0, "%s: V must be > 0 and E >= 0 (V=%d E=%lld)", who, V, (long long)E);
+    G2V_REQUIRE(L >= 1 && L <= 4096, "%s: lenPath must be in [1, 4096] (got %d)", who, L);
+    G2V_REQUIRE(walker_stride >= 1 && walker_begin >= 0, "%s: bad walker range", who);
+    G2V_REQUIRE(E < (1ll << 31), "%s: E must fit int32", who);
+    const int64_t n_walkers =
+        walker_end > walker_begin ? (walker_end - walker_begin + walker_stride - 1) / walker_stride : 0;
+    if (n_walkers == 0) return 0;                                 // empty range: nothing to write
+    G2V_REQUIRE(g.rows && out_nodes && out_len && workspace, "%s: null pointer", who);
+    G2V_REQUIRE(E == 0 || (g.edges && (layout != LAY_CSR || g.qw)), "%s: null edge arrays with E > 0", who);
+    G2V_REQUIRE(layout == LAY_CSR || layout == LAY_E8 || (layout == LAY_E4 && V <= 65536), "%s: bad layout %d", who, layout);
+    DeviceProps dp;
+    if (device_props(&dp)) return 1;
+    G2V_REQUIRE(dp.cc_major == 10, "%s: needs an sm_100 device (found sm_%d%d)", who, dp.cc_major, dp.cc_minor);
+
+    const bool canon = out_key != nullptr;
+    // path buffer: L ints, rounded to 32 (visit order) or to the power of two the bitonic network needs
+    int Lpad = (L + 31) & ~31;
+    if (canon) { Lpad = 32; while (Lpad < L) Lpad <<= 1; }
+    // visited set per walker: a V-bit bitmap when a CTA's bitmaps fit 56 KB (>= 4 CTAs per SM), else a hash set
+    const int bm_words = (V + 31) / 32;
+    const char *force = getenv("G2V_WALK_VISITED");               // test hook: "hash" / "bitmap"
+    int Hh = 64, hshift = 26;                                     // hash set: >= 3L slots, power of two
+    while (Hh < 3 * L) { Hh <<= 1; --hshift; }
+    const size_t per_warp = (size_t)kWalkWarps * sizeof(int32_t);
+    const size_t bm_smem = per_warp * (Lpad + bm_words), hash_smem = per_warp * (Lpad + Hh);
+    bool bitmap = bm_smem <= 56 * 1024 || bm_smem <= hash_smem;   // occupancy first, then whichever is smaller
+    if (force && force[0] == 'h') bitmap = false;
+    if (force && force[0] == 'b' && bm_smem <= (size_t)dp.max_smem_optin) bitmap = true;
+    const int H = bitmap ? bm_words : Hh;
+    const size_t smem = per_warp * (size_t)(Lpad + H);
+    G2V_REQUIRE(smem <= (size_t)dp.max_smem_optin, "%s: lenPath %d needs %zu B of shared memory", who, L, smem);
+    static const walk_kern_t table[2][3][2] = {
+        {{walk_kernel<false, LAY_CSR, false>, walk_kernel<false, LAY_CSR, true>},
+         {walk_kernel<false, LAY_E8, false>, walk_kernel<false, LAY_E8, true>},
+         {walk_kernel<false, LAY_E4, false>, walk_kernel<false, LAY_E4, true>}},
+        {{walk_kernel<true, LAY_CSR, false>, walk_kernel<true, LAY_CSR, true>},
+         {walk_kernel<true, LAY_E8, false>, walk_kernel<true, LAY_E8, true>},
+         {walk_kernel<true, LAY_E4, false>, walk_kernel<true, LAY_E4, true>}}};
+    walk_kern_t kern = table[bitmap][layout][canon];
+    // per-device function attributes (set on every call: the process may have switched device)
+    G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
+    G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    G2V_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWalkWarps * 32, smem));
+    G2V_REQUIRE(per_sm > 0, "%s: kernel does not fit on an SM", who);
+    int64_t grid = (int64_t)dp.sm_count * per_sm;                 // persistent: whole chip resident
+    const int64_t need = (n_walkers + kWalkWarps - 1) / kWalkWarps;
+    if (grid > need) grid = need;
+    G2V_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(unsigned long long), st));
+    kern<<<(unsigned)grid, kWalkWarps * 32, smem, st>>>(g, V, L, Lpad, H, hshift, seed, group, walker_begin, n_walkers,
+                                                        walker_stride, out_nodes, out_len,
+                                                        reinterpret_cast<unsigned long long *>(out_key),
+                                                        (unsigned long long *)workspace);
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
 }
 
 }  // namespace g2v
@@ -262,70 +392,60 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
                                int64_t walker_begin, int64_t walker_end, int64_t walker_stride,
                                int32_t *out_nodes, int32_t *out_len, void *workspace,
                                void *stream) {
-    G2V_REQUIRE(V > 0 && E >= 0, "g2v_walk_launch: V must be > 0 and E >= 0 (V=%d E=%lld)", V, (long long)E);
-    G2V_REQUIRE(L >= 1 && L <= 4096, "g2v_walk_launch: lenPath must be in [1, 4096] (got %d)", L);
-    G2V_REQUIRE(walker_stride >= 1 && walker_begin >= 0, "g2v_walk_launch: bad walker range");
-    const int64_t n_walkers =
-        walker_end > walker_begin ? (walker_end - walker_begin + walker_stride - 1) / walker_stride : 0;
-    if (n_walkers == 0) return 0;                                 // empty range: nothing to write
-    G2V_REQUIRE(rowptr && out_nodes && out_len && workspace, "g2v_walk_launch: null pointer");
-    G2V_REQUIRE(E == 0 || (col && qw), "g2v_walk_launch: null col/qw with E > 0");
+    WalkGraphPtrs g{rowptr, col, qw};
+    return launch_walk(g, LAY_CSR, V, E, L, seed, group, walker_begin, walker_end, walker_stride, out_nodes, out_len,
+                       nullptr, workspace, (cudaStream_t)stream, "g2v_walk_launch");
+}
+
+extern "C" int g2v_walk_packed_bytes(int32_t V, int64_t E, size_t *rows_bytes, size_t *edges_bytes) {
+    G2V_REQUIRE(V > 0 && E >= 0 && rows_bytes && edges_bytes, "g2v_walk_packed_bytes: bad arguments");
+    *rows_bytes = sizeof(int2) * (size_t)V;
+    *edges_bytes = sizeof(uint2) * (size_t)(E + 2);
+    return 0;
+}
+
+extern "C" int g2v_walk_prepare(const int32_t *rowptr, const int32_t *col, const uint32_t *qw, int32_t V, int64_t E,
+                                void *rows, void *edges, int32_t *layout_out, void *workspace, void *stream) {
+    G2V_REQUIRE(V > 0 && E >= 0 && E < (1ll << 31), "g2v_walk_prepare: bad sizes (V=%d E=%lld)", V, (long long)E);
+    G2V_REQUIRE(rowptr && rows && edges && layout_out && workspace && (E == 0 || (col && qw)), "g2v_walk_prepare: null pointer");
     DeviceProps dp;
     if (device_props(&dp)) return 1;
-    G2V_REQUIRE(dp.cc_major == 10, "g2v_walk_launch: needs an sm_100 device (found sm_%d%d)", dp.cc_major, dp.cc_minor);
-
-    // lanes per walker.  A full warp per walker is the fastest width on every graph measured -- syn10k
-    // (mean degree 50): 3.3 ms at 32 lanes, 4.5 ms at 16, 6.0 ms at 8; ex_* (mean degree 3.4, 62 % of the
-    // walks are singletons): 0.35 / 0.51 / 0.76 ms (profiles/README.md) -- so 8 and 16 are reachable only
-    // through the G2V_WALK_TILE hook that the tests use.
-    const double mean_deg = (double)E / (double)V;
-    const char *ft = getenv("G2V_WALK_TILE");
-    int tile = 32;
-    if (ft && (atoi(ft) == 8 || atoi(ft) == 16 || atoi(ft) == 32)) tile = atoi(ft);
-    const int nt = 32 / tile;
-    // visited set per walker: a V-bit bitmap when a CTA's bitmaps fit 56 KB (>= 4 CTAs per SM), else a hash set
-    const int Lpad = (L + 31) & ~31;
-    const int bm_words = (V + 31) / 32;
-    const char *force = getenv("G2V_WALK_VISITED");               // test hook: "hash" / "bitmap"
-    int Hh = 64, hshift = 26;                                     // hash set: >= 3L slots, power of two
-    while (Hh < 3 * L) { Hh <<= 1; --hshift; }
-    const size_t per_tile = (size_t)kWalkWarps * nt * sizeof(int32_t);
-    const size_t bm_smem = per_tile * (Lpad + bm_words), hash_smem = per_tile * (Lpad + Hh);
-    bool bitmap = bm_smem <= 56 * 1024 || bm_smem <= hash_smem;   // occupancy first, then whichever is smaller
-    if (force && force[0] == 'h') bitmap = false;
-    const int H = bitmap ? bm_words : Hh;
-    const size_t smem = (size_t)kWalkWarps * nt * (Lpad + H) * sizeof(int32_t);
-    G2V_REQUIRE(smem <= (size_t)dp.max_smem_optin, "g2v_walk_launch: lenPath %d needs %zu B of shared memory", L, smem);
     cudaStream_t st = (cudaStream_t)stream;
-    typedef void (*kern_t)(const int32_t *, const int32_t *, const uint32_t *, int32_t, int32_t, int32_t, int32_t,
-                           int32_t, uint64_t, uint32_t, int64_t, int64_t, int64_t, int32_t *, int32_t *,
-                           unsigned long long *);
-    // chunks cached in registers: 2 when rows mostly fit 64 neighbours, 4 otherwise (G2V_WALK_KC overrides)
-    const char *fk = getenv("G2V_WALK_KC");
-    int kc = mean_deg <= 64.0 ? 2 : 4;   // measured: syn10k (deg 50) 2.96 vs 3.33 ms, syn20k (deg 100) 8.80 vs 8.18 ms
-    if (fk && (atoi(fk) == 2 || atoi(fk) == 4)) kc = atoi(fk);
-    if (tile != 32) kc = 4;
-    static const kern_t table[2][4] = {
-        {walk_kernel<false, 8, 4>, walk_kernel<false, 16, 4>, walk_kernel<false, 32, 4>, walk_kernel<false, 32, 2>},
-        {walk_kernel<true, 8, 4>, walk_kernel<true, 16, 4>, walk_kernel<true, 32, 4>, walk_kernel<true, 32, 2>}};
-    const int ti = tile == 8 ? 0 : (tile == 16 ? 1 : (kc == 4 ? 2 : 3));
-    kern_t kern = table[bitmap][ti];
-    // per-device function attributes (set on every call: the process may have switched device)
-    G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
-    G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int per_sm = 0;
-    G2V_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWalkWarps * 32, smem));
-    G2V_REQUIRE(per_sm > 0, "g2v_walk_launch: kernel does not fit on an SM");
-    int64_t grid = (int64_t)dp.sm_count * per_sm;                 // persistent: whole chip resident
-    const int64_t need = (n_walkers + kWalkWarps * nt - 1) / (kWalkWarps * nt);
-    if (grid > need) grid = need;
-    G2V_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(unsigned long long), st));
-    kern<<<(unsigned)grid, kWalkWarps * 32, smem, st>>>(
-        rowptr, col, qw, V, L, Lpad, H, hshift, seed, group, walker_begin, n_walkers, walker_stride,
-        out_nodes, out_len, (unsigned long long *)workspace);
+    int layout = LAY_E8;
+    const char *force = getenv("G2V_WALK_LAYOUT");                // test hook: "e8" / "e4" (e4 only if eligible)
+    if (V <= 65536 && !(force && force[1] == '8')) {
+        int32_t *flag = reinterpret_cast<int32_t *>(workspace) + 8;   // the ticket lives in the first 8 bytes
+        int32_t h = 0;
+        G2V_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
+        if (E > 0) {
+            int64_t blocks = (E + 255) / 256;
+            if (blocks > (int64_t)dp.sm_count * 8) blocks = (int64_t)dp.sm_count * 8;
+            walk_range_kernel<<<(unsigned)blocks, 256, 0, st>>>(qw, E, flag);
+            G2V_CUDA_OK(cudaGetLastError());
+            count_launch();
+        }
+        G2V_CUDA_OK(cudaMemcpyAsync(&h, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        G2V_CUDA_OK(cudaStreamSynchronize(st));                   // setup, once per graph
+        if (h == 0) layout = LAY_E4;
+    }
+    int64_t work = E + 2 > V ? E + 2 : V;
+    int64_t blocks = (work + 255) / 256;
+    if (blocks > (int64_t)dp.sm_count * 8) blocks = (int64_t)dp.sm_count * 8;
+    walk_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, qw, V, E, layout, reinterpret_cast<int2 *>(rows), edges);
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
+    *layout_out = layout;
     return 0;
+}
+
+extern "C" int g2v_walk_launch_packed(const void *rows, const void *edges, int32_t layout, int32_t V, int64_t E,
+                                      int32_t L, uint64_t seed, uint32_t group, int64_t walker_begin,
+                                      int64_t walker_end, int64_t walker_stride, int32_t *out_nodes, int32_t *out_len,
+                                      int64_t *out_key, void *workspace, void *stream) {
+    G2V_REQUIRE(layout == LAY_E8 || layout == LAY_E4, "g2v_walk_launch_packed: layout must come from g2v_walk_prepare");
+    WalkGraphPtrs g{reinterpret_cast<const int32_t *>(rows), edges, nullptr};
+    return launch_walk(g, layout, V, E, L, seed, group, walker_begin, walker_end, walker_stride, out_nodes, out_len,
+                       out_key, workspace, (cudaStream_t)stream, "g2v_walk_launch_packed");
 }
 
 extern "C" int g2v_walk_host(const int32_t *rowptr, const int32_t *col, const uint32_t *qw,
@@ -335,30 +455,35 @@ extern "C" int g2v_walk_host(const int32_t *rowptr, const int32_t *col, const ui
     G2V_REQUIRE(V > 0 && E >= 0 && L >= 1 && walker_stride >= 1, "g2v_walk_host: bad arguments");
     const int64_t n = walker_end > walker_begin ? (walker_end - walker_begin + walker_stride - 1) / walker_stride : 0;
     if (n == 0) return 0;
-    int32_t *d_rowptr = nullptr, *d_col = nullptr, *d_nodes = nullptr, *d_len = nullptr;
-    uint32_t *d_qw = nullptr;
-    void *d_ws = nullptr;
+    // ONE device slab: rowptr | col | qw | packed rows | packed edges | nodes | len | workspace
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t Ee = (size_t)(E > 0 ? E : 1);
+    const size_t o_rp = take(sizeof(int32_t) * (size_t)(V + 1)), o_col = take(sizeof(int32_t) * Ee),
+                 o_qw = take(sizeof(uint32_t) * Ee), o_rows = take(sizeof(int2) * (size_t)V),
+                 o_edges = take(sizeof(uint2) * (size_t)(E + 2)), o_nodes = take(sizeof(int32_t) * (size_t)n * (size_t)L),
+                 o_len = take(sizeof(int32_t) * (size_t)n), o_ws = take(g2v_walk_workspace_bytes());
+    char *d = nullptr;
     int rc = 1;
     cudaStream_t st = nullptr;
     do {
         if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) break;
-        if (cudaMalloc(&d_rowptr, sizeof(int32_t) * (size_t)(V + 1)) != cudaSuccess) break;
-        if (cudaMalloc(&d_col, sizeof(int32_t) * (size_t)(E > 0 ? E : 1)) != cudaSuccess) break;
-        if (cudaMalloc(&d_qw, sizeof(uint32_t) * (size_t)(E > 0 ? E : 1)) != cudaSuccess) break;
-        if (cudaMalloc(&d_nodes, sizeof(int32_t) * (size_t)n * (size_t)L) != cudaSuccess) break;
-        if (cudaMalloc(&d_len, sizeof(int32_t) * (size_t)n) != cudaSuccess) break;
-        if (cudaMalloc(&d_ws, g2v_walk_workspace_bytes()) != cudaSuccess) break;
-        if (cudaMemcpyAsync(d_rowptr, rowptr, sizeof(int32_t) * (size_t)(V + 1), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+        if (cudaMalloc(&d, off) != cudaSuccess) break;
+        if (cudaMemcpyAsync(d + o_rp, rowptr, sizeof(int32_t) * (size_t)(V + 1), cudaMemcpyHostToDevice, st) != cudaSuccess) break;
         if (E > 0) {
-            if (cudaMemcpyAsync(d_col, col, sizeof(int32_t) * (size_t)E, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
-            if (cudaMemcpyAsync(d_qw, qw, sizeof(uint32_t) * (size_t)E, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+            if (cudaMemcpyAsync(d + o_col, col, sizeof(int32_t) * (size_t)E, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+            if (cudaMemcpyAsync(d + o_qw, qw, sizeof(uint32_t) * (size_t)E, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
         }
-        rc = g2v_walk_launch(d_rowptr, d_col, d_qw, V, E, L, seed, group, walker_begin, walker_end,
-                             walker_stride, d_nodes, d_len, d_ws, st);
+        int32_t layout = LAY_E8;
+        rc = g2v_walk_prepare((int32_t *)(d + o_rp), (int32_t *)(d + o_col), (uint32_t *)(d + o_qw), V, E, d + o_rows,
+                              d + o_edges, &layout, d + o_ws, st);
+        if (rc) break;
+        rc = g2v_walk_launch_packed(d + o_rows, d + o_edges, layout, V, E, L, seed, group, walker_begin, walker_end,
+                                    walker_stride, (int32_t *)(d + o_nodes), (int32_t *)(d + o_len), nullptr, d + o_ws, st);
         if (rc) break;
         rc = 1;
-        if (cudaMemcpyAsync(out_nodes, d_nodes, sizeof(int32_t) * (size_t)n * (size_t)L, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
-        if (cudaMemcpyAsync(out_len, d_len, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (cudaMemcpyAsync(out_nodes, d + o_nodes, sizeof(int32_t) * (size_t)n * (size_t)L, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+        if (cudaMemcpyAsync(out_len, d + o_len, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
         if (cudaStreamSynchronize(st) != cudaSuccess) break;
         rc = 0;
     } while (0);
@@ -366,7 +491,7 @@ extern "C" int g2v_walk_host(const int32_t *rowptr, const int32_t *col, const ui
         cudaError_t e = cudaGetLastError();
         set_error("g2v_walk_host: CUDA failure: %s", cudaGetErrorString(e));
     }
-    cudaFree(d_rowptr); cudaFree(d_col); cudaFree(d_qw); cudaFree(d_nodes); cudaFree(d_len); cudaFree(d_ws);
+    cudaFree(d);
     if (st) cudaStreamDestroy(st);
     return rc;
 }

@@ -53,7 +53,23 @@ class WalkGraph:
         if self.qw.shape[0] != self.E:
             raise ValueError("col / weight length mismatch")
         self.device = device
-        self._ws = torch.zeros(max(int(_capi.load().g2v_walk_workspace_bytes()), 8), dtype=torch.uint8, device=device)
+        lib = _capi.load()
+        self._ws = torch.zeros(max(int(lib.g2v_walk_workspace_bytes()), 64), dtype=torch.uint8, device=device)
+        # packed layouts, built once per graph by g2v_walk_prepare: rows = {begin, end} pairs, edges = {col, qw}
+        # pairs (layout 1) or 16+16-bit words, two neighbours per 8-byte load (layout 2: V <= 65536 and weights in
+        # the |PCC| range [0.5, 1])
+        import ctypes
+        rb, eb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        _capi.check(lib.g2v_walk_packed_bytes(self.V, self.E, ctypes.byref(rb), ctypes.byref(eb)), "g2v_walk_packed_bytes")
+        self.rows = torch.empty(max(rb.value, 8), dtype=torch.uint8, device=device)
+        self.edges = torch.empty(max(eb.value, 8), dtype=torch.uint8, device=device)
+        lay = ctypes.c_int32(0)
+        with torch.cuda.device(device):
+            st = torch.cuda.current_stream().cuda_stream
+            _capi.check(lib.g2v_walk_prepare(self.rowptr.data_ptr(), self.col.data_ptr(), self.qw.data_ptr(), self.V,
+                                             self.E, self.rows.data_ptr(), self.edges.data_ptr(), ctypes.byref(lay),
+                                             self._ws.data_ptr(), st), "g2v_walk_prepare")
+        self.layout = int(lay.value)
 
     @classmethod
     def from_dense(cls, adjMat, device=None):
@@ -70,26 +86,43 @@ def num_walkers(V, reps, begin=0, end=None, stride=1):
 
 
 def generate_paths(g, len_path, reps, seed=0, group=0, walker_begin=0, walker_end=None, walker_stride=1,
-                   out=None):
+                   out=None, canonical=False, plain_csr=False):
     """Run walkers w = walker_begin + i*walker_stride < walker_end (w = rep*V + src) of graph ``g``.
 
     Returns (nodes int32 [n, len_path] in VISIT order padded with -1, lens int32 [n]) as device
-    tensors; asynchronous on the current stream."""
+    tensors; asynchronous on the current stream.
+
+    ``canonical=True`` fuses ``path = tuple(sorted(path))`` (G2Vec.py:345) into the sampler: the rows come back
+    sorted ascending and padded with INT32_MAX, and a third tensor holds their 64-bit keys (what
+    ``paths.canonical_rows`` would otherwise compute from the visit-order rows in a second kernel).
+    ``plain_csr=True`` runs the kernel on the unpacked CSR arrays through ``g2v_walk_launch``."""
     lib = _capi.load()
     end = g.V * reps if walker_end is None else walker_end
     n = num_walkers(g.V, reps, walker_begin, end, walker_stride)
     if out is None:
         nodes = torch.empty((n, len_path), dtype=torch.int32, device=g.device)
         lens = torch.empty((n,), dtype=torch.int32, device=g.device)
+        key = torch.empty((n,), dtype=torch.int64, device=g.device) if canonical else None
     else:
-        nodes, lens = out
+        nodes, lens = out[0], out[1]
+        key = out[2] if canonical else None
         assert nodes.shape == (n, len_path) and lens.shape == (n,) and nodes.is_contiguous()
     with torch.cuda.device(g.device):
         st = torch.cuda.current_stream().cuda_stream
-        rc = lib.g2v_walk_launch(g.rowptr.data_ptr(), g.col.data_ptr(), g.qw.data_ptr(), g.V, g.E, int(len_path),
-                                 int(seed) & (2**64 - 1), int(group), int(walker_begin), int(end),
-                                 int(walker_stride), nodes.data_ptr(), lens.data_ptr(), g._ws.data_ptr(), st)
+        if plain_csr:
+            if canonical:
+                raise ValueError("canonical rows need the packed graph")
+            rc = lib.g2v_walk_launch(g.rowptr.data_ptr(), g.col.data_ptr(), g.qw.data_ptr(), g.V, g.E, int(len_path),
+                                     int(seed) & (2**64 - 1), int(group), int(walker_begin), int(end),
+                                     int(walker_stride), nodes.data_ptr(), lens.data_ptr(), g._ws.data_ptr(), st)
+        else:
+            rc = lib.g2v_walk_launch_packed(g.rows.data_ptr(), g.edges.data_ptr(), g.layout, g.V, g.E, int(len_path),
+                                            int(seed) & (2**64 - 1), int(group), int(walker_begin), int(end),
+                                            int(walker_stride), nodes.data_ptr(), lens.data_ptr(),
+                                            0 if key is None else key.data_ptr(), g._ws.data_ptr(), st)
     _capi.check(rc, "g2v_walk_launch")
+    if canonical:
+        return nodes, lens, key
     return nodes, lens
 
 

@@ -71,7 +71,26 @@ int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const uint32_t *q
                     int64_t walker_end, int64_t walker_stride, int32_t *out_nodes,
                     int32_t *out_len, void *workspace, void *stream);
 
-/* Same, HOST pointers in and out (allocates, copies, launches, copies back, frees). */
+/* Packed graph layouts (built once per graph; the graph is static across all repetitions, G2Vec.py:348-351).
+ * g2v_walk_prepare turns the CSR arrays (device pointers) into
+ *   rows  [V]  int32 pairs {begin, end} of each node's out-edges                (g2v_walk_packed_bytes: rows_bytes)
+ *   edges      layout 1: uint32 pairs {col, qw} [E], one 8-byte load per neighbour;
+ *              layout 2: uint32 col | (qw - 32768) << 16 [E] -- chosen when V <= 65536 and every
+ *              32768 <= qw <= 65536 (weights |PCC| in [0.5, 1], G2Vec.py:389): one 8-byte load brings two
+ *              neighbours per lane                                              (edges_bytes covers both)
+ * and returns the layout chosen through *layout_out (a host int; the call synchronises the stream once).
+ * g2v_walk_launch_packed is g2v_walk_launch on the packed graph.  With out_key != NULL it also performs
+ * `path = tuple(sorted(path))` (G2Vec.py:345) in the same kernel: out_nodes rows are then SORTED ascending and
+ * padded with INT32_MAX, and out_key [n] receives the 64-bit row key g2v_paths_canonicalise would compute. */
+int g2v_walk_packed_bytes(int32_t V, int64_t E, size_t *rows_bytes, size_t *edges_bytes);
+int g2v_walk_prepare(const int32_t *rowptr, const int32_t *col, const uint32_t *qw, int32_t V, int64_t E,
+                     void *rows, void *edges, int32_t *layout_out, void *workspace, void *stream);
+int g2v_walk_launch_packed(const void *rows, const void *edges, int32_t layout, int32_t V, int64_t E, int32_t L,
+                           uint64_t seed, uint32_t group, int64_t walker_begin, int64_t walker_end,
+                           int64_t walker_stride, int32_t *out_nodes, int32_t *out_len, int64_t *out_key,
+                           void *workspace, void *stream);
+
+/* Same, HOST pointers in and out (one device slab: copies in, packs, launches, copies back, frees). */
 int g2v_walk_host(const int32_t *rowptr, const int32_t *col, const uint32_t *qw, int32_t V,
                   int64_t E, int32_t L, uint64_t seed, uint32_t group, int64_t walker_begin,
                   int64_t walker_end, int64_t walker_stride, int32_t *out_nodes,
@@ -118,6 +137,31 @@ int g2v_cbow_eval(const int32_t *rowptr, const int32_t *gene, const uint8_t *lab
                   const int32_t *win, int64_t win_begin, int64_t n_win, const float *W_ih,
                   const float *W_ho, int64_t *n_correct, int32_t V, int32_t D, int32_t reduce,
                   void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * HOT PATH 2 for tables larger than the L2 (csrc/g2v_cbow_slab.cu): the same step as g2v_cbow_fwdbwd /
+ * g2v_cbow_eval, processed gene slab by gene slab so that the gathered rows and the gradient rows stay
+ * L2-resident.  Needs windows whose gene lists are strictly ascending (tuple(sorted(path)), G2Vec.py:345).
+ *
+ * g2v_cbow_slab_plan: number of slabs for a [V, D] table on the current device (1 = table + gradient fit
+ *   the L2 together, or D is not 128/256/512: use g2v_cbow_fwdbwd).
+ * g2v_cbow_slab_workspace_bytes / g2v_cbow_slab_setup: per window list (win/win_begin/n_win as in
+ *   g2v_cbow_fwdbwd; the list is static across steps, G2Vec.py:262-264), records where each window's sorted gene
+ *   list crosses the slab boundaries.  Synchronises the stream once; fails on an unsorted window.
+ * g2v_cbow_fwdbwd_slabs / g2v_cbow_eval_slabs: same accumulation semantics as g2v_cbow_fwdbwd / g2v_cbow_eval,
+ *   for the list the workspace was set up with.
+ * ------------------------------------------------------------------------------------- */
+int g2v_cbow_slab_plan(int32_t V, int32_t D, int32_t *n_slabs);
+size_t g2v_cbow_slab_workspace_bytes(int64_t n_win, int32_t D, int32_t n_slabs);
+int g2v_cbow_slab_setup(const int32_t *rowptr, const int32_t *gene, const int32_t *win, int64_t win_begin,
+                        int64_t n_win, int32_t V, int32_t n_slabs, void *workspace, void *stream);
+int g2v_cbow_fwdbwd_slabs(const int32_t *gene, const uint8_t *label, const int32_t *win, int64_t win_begin,
+                          int64_t n_win, float inv_n_total, const float *W_ih, const float *W_ho, float *g_ih,
+                          float *g_ho, double *loss_sum, int64_t *n_correct, int32_t V, int32_t D, int32_t reduce,
+                          int32_t n_slabs, void *workspace, void *stream);
+int g2v_cbow_eval_slabs(const int32_t *gene, const uint8_t *label, const int32_t *win, int64_t win_begin,
+                        int64_t n_win, const float *W_ih, const float *W_ho, int64_t *n_correct, int32_t V,
+                        int32_t D, int32_t reduce, int32_t n_slabs, void *workspace, void *stream);
 
 /* One full-batch step from HOST buffers: uploads the windows and the parameters/optimizer
  * state, runs fwdbwd + update, downloads the updated parameters/state, the loss sum and the

@@ -22,18 +22,21 @@ def main():
     import oracle
     from tests import helpers
 
-    # walks: bitmap + hash, every tile width / cached-chunk count, long rows (tail path)
+    # walks: bitmap + hash, every edge layout, visit order and fused canonical epilogue
     rp, col, w = helpers.random_graph(300, 40, seed=3, dead_frac=0.2)
     q = graph.quantise_weights(w)
     want, wl = oracle.walks(rp, col, q, 20, 5, 1, 0, 600)
     for vis in ("bitmap", "hash"):
-        for tile, kc in (("32", "2"), ("32", "4"), ("16", "4"), ("8", "4")):
-            os.environ.update(G2V_WALK_VISITED=vis, G2V_WALK_TILE=tile, G2V_WALK_KC=kc)
+        for layout in ("csr", "e8", "e4"):
+            os.environ.update(G2V_WALK_VISITED=vis, G2V_WALK_LAYOUT="e8" if layout == "e8" else "e4")
             g = g2v.WalkGraph(rp, col, qw=q)
-            nodes, lens = g2v.generate_paths(g, 20, 2, seed=5, group=1)
+            nodes, lens = g2v.generate_paths(g, 20, 2, seed=5, group=1, plain_csr=(layout == "csr"))
             torch.cuda.synchronize()
-            assert (nodes.cpu().numpy() == want).all() and (lens.cpu().numpy() == wl).all(), (vis, tile, kc)
-    for k in ("G2V_WALK_VISITED", "G2V_WALK_TILE", "G2V_WALK_KC"):
+            assert (nodes.cpu().numpy() == want).all() and (lens.cpu().numpy() == wl).all(), (vis, layout)
+            if layout != "csr":
+                rows, _, key = g2v.generate_paths(g, 20, 2, seed=5, group=1, canonical=True)
+                torch.cuda.synchronize()
+    for k in ("G2V_WALK_VISITED", "G2V_WALK_LAYOUT"):
         os.environ.pop(k)
     a, al = g2v.generate_paths_host(rp, col, q, 20, 2, seed=5, group=1)
     assert (a == want).all()

@@ -451,3 +451,68 @@ def test_cbow_full_size_properties(g2v):
     a = g2v.train_cbow(rowptr, gene.ravel(), label, V, D, 0.005, algo="rows", **kw)
     b = g2v.train_cbow(rowptr, gene.ravel(), label, V, D, 0.005, algo="rank1", **kw)
     assert rel_max(a, b) < RTOL_VEC
+
+
+# ------------------------------------------------------------- gene-slab passes (tables larger than the L2)
+@pytest.mark.parametrize("D,reduce,slabs,group", [(128, "sum", 2, 1), (128, "sum", 5, 2), (256, "sum", 3, 2),
+                                                  (512, "sum", 7, 3), (512, "mean", 4, 2), (128, "mean", 3, 1)])
+def test_slab_passes_equal_oracle_and_fused_kernel(g2v, monkeypatch, D, reduce, slabs, group):
+    """csrc/g2v_cbow_slab.cu: the step processed gene slab by gene slab (forced here on a small table with
+    G2V_CBOW_SLABS) gives the oracle's gradients, loss and accuracy counts, and the same update as the fused
+    single-pass kernel; windows that have no gene in a slab, empty windows and a window list with an offset."""
+    import torch
+    V, N = 700, 2500
+    rowptr, gene, label = helpers.random_windows(N, V, 1, 60, seed=D + slabs)
+    rowptr[7] = rowptr[6]                                          # an empty window
+    gene = gene[:rowptr[N - 1]].copy(); rowptr[N] = rowptr[N - 1]  # and an empty last one
+    W0, Wo0 = helpers.init_weights(V, D, 5)
+    rs = np.random.RandomState(1)
+    win = rs.permutation(N)[:2000].astype(np.int64)
+    monkeypatch.setenv("G2V_CBOW_SLABS", str(slabs))
+    monkeypatch.setenv("G2V_CBOW_SLAB_FWD_GROUP", str(group))
+    m = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, reduce=reduce, lr=0.005)
+    wd = torch.from_numpy(win.astype(np.int32)).cuda()
+    assert m.prepare_slabs(wd) and m._n_slabs == slabs
+    m.fwdbwd(wd, len(win))
+    m.evaluate(wd, 2)
+    torch.cuda.synchronize()
+    acc = m.acc.cpu()
+    g_ih, g_ho = m.g_ih.cpu().numpy().copy(), m.g_ho.cpu().numpy().copy()
+    monkeypatch.delenv("G2V_CBOW_SLABS")
+    f = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, reduce=reduce, lr=0.005)      # fused single-pass kernel
+    f.fwdbwd(wd, len(win))
+    f.evaluate(wd, 2)
+    torch.cuda.synchronize()
+    facc = f.acc.cpu()
+    assert rel_max(g_ih, f.g_ih.cpu().numpy()) < 2e-5 and rel_max(g_ho, f.g_ho.cpu().numpy()) < 2e-5
+    assert abs(int(acc[1]) - int(facc[1])) <= 1 and abs(int(acc[2]) - int(facc[2])) <= 1
+    assert abs(m.loss_sum(acc) - f.loss_sum(facc)) < 1e-5 * max(1.0, abs(f.loss_sum(facc)))
+    if reduce == "sum":
+        o_gih, o_gho, o_loss, o_nc = oracle.cbow_grad(rowptr, gene, label, win, len(win), W0, Wo0)
+        assert rel_max(g_ih, o_gih) < 2e-5 and rel_max(g_ho, o_gho) < 2e-5
+        assert abs(m.loss_sum(acc) / len(win) - o_loss) < 1e-5 * max(1.0, abs(o_loss))
+        assert abs(int(acc[1]) - o_nc) <= 2 and abs(int(acc[2]) - o_nc) <= 2
+    m.update(); f.update()
+    torch.cuda.synchronize()
+    assert rel_max(m.W_ih.cpu().numpy(), f.W_ih.cpu().numpy()) < RTOL_VEC
+
+
+def test_slab_training_run_equals_the_reference_golden(g2v, monkeypatch):
+    """The whole loop (train_cbow: CUDA-graph replays, early stop) on slab passes against the reference run."""
+    monkeypatch.setenv("G2V_CBOW_SLABS", "3")
+    g = helpers.cbow_golden("cbow_ex.npz")
+    got, info = g2v.train_cbow(g["rowptr"], g["gene"], g["label"], g["V"], g["D"], g["lr"], max_epoch=500,
+                               seed=g["seed"], log=None, return_info=True)
+    assert info["model"]._n_slabs == 3 and len(info["model"]._slabs) == 2
+    assert info["stop_step"] == g["stop_step"]
+    assert rel_max(got, g["W_ref"]) < RTOL_VEC
+
+
+def test_slab_setup_rejects_unsorted_windows(g2v, monkeypatch):
+    import torch
+    monkeypatch.setenv("G2V_CBOW_SLABS", "2")
+    rowptr = np.array([0, 3, 5], dtype=np.int32); gene = np.array([4, 2, 9, 1, 3], dtype=np.int32)
+    W0, Wo0 = helpers.init_weights(10, 128, 0)
+    m = g2v.CbowModel(rowptr, gene, np.array([0, 1], dtype=np.uint8), 10, 128, W0, Wo0)
+    with pytest.raises(RuntimeError, match="not strictly ascending"):
+        m.prepare_slabs(None)

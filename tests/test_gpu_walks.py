@@ -153,22 +153,58 @@ def test_hash_visited_set_path(g2v, monkeypatch):
     assert (got == want).all() and (gl == wl).all() and wl.max() == 80 and wl.min() == 1
 
 
-@pytest.mark.parametrize("tile,kc", [("8", "4"), ("16", "4"), ("32", "4"), ("32", "2")])
+def sorted_rows(nodes, lens, pad):
+    out = np.full_like(nodes, pad)
+    for i, (r, n) in enumerate(zip(nodes, lens)):
+        out[i, :n] = np.sort(r[:n])
+    return out
+
+
+@pytest.mark.parametrize("layout", ["csr", "e8", "e4"])
 @pytest.mark.parametrize("vis", ["bitmap", "hash"])
-def test_every_tile_width_and_visited_set_is_bit_exact(g2v, monkeypatch, tile, kc, vis):
-    """Every kernel instantiation: 8/16/32 lanes per walker x 2/4 register-cached chunks x bitmap/hash."""
-    monkeypatch.setenv("G2V_WALK_TILE", tile)
-    monkeypatch.setenv("G2V_WALK_KC", kc)
+def test_every_layout_and_visited_set_is_bit_exact(g2v, monkeypatch, layout, vis):
+    """Every kernel instantiation: plain CSR arrays (g2v_walk_launch) / {col,qw} pairs / packed 16+16-bit edges
+    (two neighbours per lane) x bitmap / hash visited set x visit order / fused tuple(sorted(path)) epilogue."""
+    import torch
+    from g2vec_b200 import paths
     monkeypatch.setenv("G2V_WALK_VISITED", vis)
+    if layout == "e8":
+        monkeypatch.setenv("G2V_WALK_LAYOUT", "e8")
     cases = [helpers.ex_graph(1) + (80, 2), helpers.random_graph(2000, 40, seed=1, dead_frac=0.2) + (33, 3)]
     V = 300
     A = (0.5 + 0.5 * np.random.RandomState(4).rand(V, V)).astype(np.float32) + np.float32(1e-4)
     np.fill_diagonal(A, 0)
     from oracle import legacy
-    cases.append(legacy.csr_from_dense(A) + (300, 1))            # rows of 299 neighbours: tail path at every width
+    cases.append(legacy.csr_from_dense(A) + (300, 1))            # rows of 299 neighbours: register chunks + tail
     for rp, col, w, L, reps in cases:
         q = oracle.quantise_weights(w)
         n = len(rp) - 1
         want, wl = oracle.walks(rp, col, q, L, 77, 1, 0, reps * n)
-        got, gl = run_gpu(g2v, rp, col, q, L, reps, 77, 1)
+        g = g2v.WalkGraph(rp, col, qw=q)
+        packable = q.min() >= 32768 and q.max() <= 65536          # |PCC| in [0.5, 1] and V <= 65536
+        assert g.layout == (2 if (packable and layout != "e8") else 1)
+        nodes, lens = g2v.generate_paths(g, L, reps, seed=77, group=1, plain_csr=(layout == "csr"))
+        torch.cuda.synchronize()
+        got, gl = nodes.cpu().numpy(), lens.cpu().numpy()
         assert (gl == wl).all() and (got == want).all()
+        if layout != "csr":
+            # fused canonical form == sort of the visit-order rows, and its keys == g2v_paths_canonicalise's
+            rows, lens2, key = g2v.generate_paths(g, L, reps, seed=77, group=1, canonical=True)
+            rows2, key2 = paths._canon(nodes)
+            torch.cuda.synchronize()
+            assert (lens2.cpu().numpy() == wl).all()
+            assert (rows.cpu().numpy() == sorted_rows(want, wl, paths.PAD)).all()
+            assert (rows.cpu().numpy() == rows2.cpu().numpy()).all() and (key.cpu().numpy() == key2.cpu().numpy()).all()
+
+
+def test_weights_outside_the_pcc_range_take_the_pair_layout(g2v):
+    """Packed 16+16-bit edges need 32768 <= qw <= 65536; anything else (and V > 65536) uses {col, qw} pairs."""
+    rp, col, w = helpers.random_graph(500, 12, seed=8, dead_frac=0.1)
+    w = (w * np.random.RandomState(1).uniform(0.01, 3.0, size=len(w))).astype(np.float32)
+    q = oracle.quantise_weights(w)
+    assert q.min() < 32768 and q.max() > 65536
+    g = g2v.WalkGraph(rp, col, qw=q)
+    assert g.layout == 1
+    want, wl = oracle.walks(rp, col, q, 40, 3, 0, 0, 1000)
+    nodes, lens = g2v.generate_paths(g, 40, 2, seed=3, group=0)
+    assert (nodes.cpu().numpy() == want).all() and (lens.cpu().numpy() == wl).all()
