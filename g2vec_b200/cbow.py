@@ -378,86 +378,189 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
         model.prepare_slabs(va_d)
     if log:
         log("     Start training the modified CBOW with early stopping")
-    t0 = time.time()
-    before_val, before_tr = np.float32(-1.0), np.float32(0.0)
-    result = model.W_ih.clone()
-    hist, stop = [], None
-    f32 = np.float32
-    graph_ok = use_graph and dist is None and full_batch
-    acc_pin = torch.zeros(4, dtype=torch.int64).pin_memory()
-    steps = {}                               # with_train_eval -> CUDA-graph step (captured at first use)
+    if full_batch:
+        out, hist, stop = _device_loop(model, dist, tr_d, va_d, n_tr, n_va, len(tr_loc), len(va_loc), max_epoch,
+                                       early_stop, log, eval_train, use_graph)
+    else:
+        out, hist, stop = _minibatch_loop(model, dist, world, tr_d, va_d, n_tr, n_va, len(tr_loc), len(va_loc),
+                                          max_epoch, early_stop, log, batch)
+    if log:
+        log("    Optimization Finish")
+    out = out.cpu().numpy()
+    if return_info:
+        return out, {"history": hist, "stop_step": stop, "n_train": n_tr, "n_val": n_va, "model": model,
+                     "graph": bool(getattr(model, "loop_used_graph", False))}
+    return out
 
-    def eager_step(show):
+
+class _LoopLog:
+    """The host side of the reference loop body after the three session runs (G2Vec.py:268-283): log line every
+    5th step, the Epoch(stop) line, the history.  Fed one step at a time with the step's counters."""
+
+    def __init__(self, n_tr, n_va, log):
+        self.n_tr, self.n_va, self.log = n_tr, n_va, log
+        self.hist, self.t0 = [], time.time()
+        self.before_val, self.before_tr = np.float32(-1.0), np.float32(0.0)
+
+    def step(self, step, acc, shown, stopped_here):
+        f32 = np.float32
+        acc_val = f32(int(acc[2])) / f32(max(self.n_va, 1))
+        acc_tr_prev = f32(int(acc[1])) / f32(max(self.n_tr, 1))      # = ACC[tr] of step-1 (SURVEY 3.2-5)
+        acc_tr = f32(int(acc[3])) / f32(max(self.n_tr, 1)) if shown else None
+        hist, log = self.hist, self.log
+        if hist and hist[-1][2] is None:
+            hist[-1] = (hist[-1][0], hist[-1][1], float(acc_tr_prev))
+        if hist:
+            self.before_tr = hist[-1][2]                            # ACC[tr] of the previous step (G2Vec.py:281)
+        hist.append((step, float(acc_val), None if acc_tr is None else float(acc_tr)))
+        if step % 5 == 0 and log:
+            t1 = time.time()
+            log("    - Epoch: %03d\tACC[val]=%.4f\tACC[tr]=%.4f (%.3f sec)" % (step, acc_val, acc_tr, t1 - self.t0))
+            self.t0 = time.time()
+        if stopped_here:
+            if log:
+                log("    - Epoch(stop): %03d\tACC[val]=%.4f\tACC[tr]=%.4f (%.3f sec)"
+                    % (step - 1, self.before_val, self.before_tr, time.time() - self.t0))
+            return True
+        self.before_val = acc_val
+        return False
+
+
+def _device_loop(model, dist, tr_d, va_d, n_tr, n_va, n_tr_loc, n_va_loc, max_epoch, early_stop, log, eval_train,
+                 use_graph, chunk=5):
+    """Full-batch loop of G2Vec.py:262-283 with the early-stop rule, the result snapshot and the step counter on
+    the DEVICE (g2v_cbow_loop_*): the host enqueues `chunk` iterations at a time -- one CUDA-graph replay of
+    4 plain iterations + 1 that also runs the training-accuracy pass -- and synchronises once per printed line
+    instead of once per step.  Iterations enqueued after the stop are no-ops (every kernel tests ctl.stopped).
+    Multi-GPU: the all-reduces are part of the captured graph (NCCL is capturable); if capture is refused the
+    same launches run eagerly."""
+    lib, dev = model.lib, model.device
+    st = lambda: torch.cuda.current_stream(dev).cuda_stream
+    ctl = torch.zeros(8, dtype=torch.int64, device=dev)
+    hist_d = torch.zeros(max(max_epoch, 1) * 4, dtype=torch.int64, device=dev)
+    ctl_pin = torch.zeros(8, dtype=torch.int64).pin_memory()
+    hist_pin = torch.zeros(max(max_epoch, 1) * 4, dtype=torch.int64).pin_memory()
+    _capi.check(lib.g2v_cbow_loop_init(ctl.data_ptr(), int(max_epoch), int(bool(early_stop)), st()), "g2v_cbow_loop_init")
+    result = model.W_ih.clone()                  # snapshot buffer: W_ih before the step being decided
+    shown = lambda s: s % 5 == 0 or eval_train == "always"
+    info = _LoopLog(n_tr, n_va, log)
+
+    def one(show):
+        _capi.check(lib.g2v_cbow_loop_begin(ctl.data_ptr(), model.acc.data_ptr(), model.W_ih.data_ptr(),
+                                            result.data_ptr(), model.V * model.D, st()), "g2v_cbow_loop_begin")
+        if n_tr_loc:
+            model.fwdbwd(tr_d, n_tr)             # acc[1] += correct predictions with the PRE-update weights
+        if dist:
+            for g in model.grad_tensors():
+                dist.all_reduce(g)
+        model.update()
+        if n_va_loc:
+            model.evaluate(va_d, 2)
+        if show and n_tr_loc:
+            model.evaluate(tr_d, 3)
+        if dist:
+            dist.all_reduce(model.acc[1:4])
+        _capi.check(lib.g2v_cbow_loop_decide(ctl.data_ptr(), model.acc.data_ptr(), hist_d.data_ptr(), st()),
+                    "g2v_cbow_loop_decide")
+
+    def fetch():
+        ctl_pin.copy_(ctl, non_blocking=True)
+        hist_pin.copy_(hist_d, non_blocking=True)
+
+    def consume(lo, hi):
+        """Host view of steps lo..hi-1 after a sync; True when the loop is over."""
+        decided, stop_step = int(ctl_pin[1]), int(ctl_pin[2])
+        for s in range(lo, min(hi, decided)):
+            if info.step(s, hist_pin[4 * s:4 * s + 4], shown(s), s == stop_step):
+                return True
+        return bool(int(ctl_pin[0]))
+
+    _capi.check(lib.g2v_cbow_loop_attach(ctl.data_ptr()), "g2v_cbow_loop_attach")
+    try:
+        one(True); fetch()                       # step 0 eagerly: it also warms every kernel up before a capture
+        torch.cuda.current_stream(dev).synchronize()
+        done, over = 1, consume(0, 1)
+        graph, graph_failed = None, not use_graph
+        while not over and done < max_epoch:
+            k = min(chunk, max_epoch - done)
+            pattern = [shown(done + i) for i in range(k)]
+            if k == chunk and not graph_failed and graph is None:
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    t_before = model.t
+                    with torch.cuda.graph(g):
+                        for sh in pattern:
+                            one(sh)
+                        fetch()
+                    model.t = t_before           # capture records, it does not execute
+                    graph, graph_pattern = g, pattern
+                except Exception:
+                    if dist is None:
+                        raise
+                    graph_failed = True          # collectives not capturable here: same launches, eagerly
+            if graph is not None and k == chunk and pattern == graph_pattern:
+                model.t += k
+                graph.replay()
+            else:
+                for sh in pattern:
+                    one(sh)
+                fetch()
+            torch.cuda.current_stream(dev).synchronize()        # one host sync per `chunk` steps
+            over = consume(done, done + k)
+            done += k
+        stop = int(ctl_pin[2]) if int(ctl_pin[2]) >= 0 else None
+        if stop is None and info.hist and info.hist[-1][2] is None:
+            # ACC[tr] of the last step was never needed for a log line; evaluate it once for the history
+            _capi.check(lib.g2v_cbow_loop_attach(None), "g2v_cbow_loop_attach")
+            model.acc.zero_()
+            if n_tr_loc:
+                model.evaluate(tr_d, 3)
+            if dist:
+                dist.all_reduce(model.acc[1:4])
+            a = model.acc.cpu()
+            last = info.hist[-1]
+            info.hist[-1] = (last[0], last[1], float(np.float32(int(a[3])) / np.float32(max(n_tr, 1))))
+    finally:
+        _capi.check(lib.g2v_cbow_loop_attach(None), "g2v_cbow_loop_attach")
+    # stopped early: the snapshot taken before the dropping step (G2Vec.py:283,286); else the final weights
+    model.loop_used_graph = graph is not None
+    return (result if stop is not None else model.W_ih), info.hist, stop
+
+
+def _minibatch_loop(model, dist, world, tr_d, va_d, n_tr, n_va, n_tr_loc, n_va_loc, max_epoch, early_stop, log, batch):
+    """north_star's mini-batch variant: one optimizer step (and one gradient all-reduce) per batch of the shuffled
+    training list, the reference's per-epoch accuracies and early stop around it; host-driven, one sync per epoch."""
+    dev = model.device
+    info = _LoopLog(n_tr, n_va, log)
+    result = model.W_ih.clone()
+    stop = None
+    per = -(-batch // world)
+    for step in range(max_epoch):
         model.acc.zero_()
-        if full_batch:
-            if len(tr_loc):
-                model.fwdbwd(tr_d, n_tr)     # acc[1] += correct predictions with the PRE-update weights
+        for lo in range(0, -(-n_tr // world), per):             # same trip count on every rank (collectives inside)
+            nb = max(0, min(per, n_tr_loc - lo))
+            nb_tot = nb
+            if dist:
+                t_nb = torch.tensor([nb], dtype=torch.int64, device=dev); dist.all_reduce(t_nb)
+                nb_tot = int(t_nb[0])
+            model.fwdbwd(tr_d, nb_tot, win_begin=lo, n_win=nb)
             if dist:
                 for g in model.grad_tensors():
                     dist.all_reduce(g)
             model.update()
-        else:                                # mini-batches: every rank takes its 1/world slice of each batch
-            per = -(-batch // world)
-            for lo in range(0, -(-n_tr // world), per):     # same trip count on every rank (collectives inside)
-                nb = max(0, min(per, len(tr_loc) - lo))
-                nb_tot = nb
-                if dist:
-                    t_nb = torch.tensor([nb], dtype=torch.int64, device=dev); dist.all_reduce(t_nb)
-                    nb_tot = int(t_nb[0])
-                model.fwdbwd(tr_d, nb_tot, win_begin=lo, n_win=nb)
-                if dist:
-                    for g in model.grad_tensors():
-                        dist.all_reduce(g)
-                model.update()
-        if len(va_loc):
+        if n_va_loc:
             model.evaluate(va_d, 2)
-        if show and len(tr_loc):
-            model.evaluate(tr_d, 3)
+        if n_tr_loc:
+            model.evaluate(tr_d, 3)                              # acc[1] mixes weights across batches: always evaluate
         if dist:
             dist.all_reduce(model.acc[1:4])
-        return model.acc.cpu()               # the step's only host sync
-
-    for step in range(max_epoch):
-        # ACC[tr] of G2Vec.py:267 uses the post-update weights, i.e. exactly what the NEXT step's training
-        # forward computes.  It is only printed every 5th step and at the stop, so the extra
-        # forward pass is run only when its value is shown now; otherwise it arrives one step later for free.
-        # (`show` must be the same on every rank -- the counters are all-reduced -- so it never looks at `log`)
-        show = (step % 5 == 0 or step == max_epoch - 1 or eval_train == "always"
-                or not full_batch)           # with mini-batches acc[1] mixes weights: always evaluate
-        if graph_ok and step > 0:            # step 0 runs eagerly (and warms every kernel up before capture)
-            if show not in steps:
-                steps[show] = model.make_step(tr_d, n_tr, va_d, acc_pin, show)
-            steps[show]()
-            torch.cuda.current_stream().synchronize()            # the step's only host sync
-            acc = acc_pin.clone()
-        else:
-            acc = eager_step(show)
-        acc_val = f32(int(acc[2])) / f32(max(n_va, 1))
-        acc_tr_prev = f32(int(acc[1])) / f32(max(n_tr, 1))      # = ACC[tr] of step-1
-        acc_tr = f32(int(acc[3])) / f32(max(n_tr, 1)) if show else None
-        if hist and hist[-1][2] is None:
-            hist[-1] = (hist[-1][0], hist[-1][1], float(acc_tr_prev))
-        if hist:
-            before_tr = hist[-1][2]                             # ACC[tr] of the previous step (G2Vec.py:281)
-        hist.append((step, float(acc_val), None if acc_tr is None else float(acc_tr)))
-        if step % 5 == 0 and log:
-            t1 = time.time()
-            log("    - Epoch: %03d\tACC[val]=%.4f\tACC[tr]=%.4f (%.3f sec)" % (step, acc_val, acc_tr, t1 - t0))
-            t0 = time.time()
-        if early_stop and acc_val < before_val:
-            if log:
-                log("    - Epoch(stop): %03d\tACC[val]=%.4f\tACC[tr]=%.4f (%.3f sec)"
-                    % (step - 1, before_val, before_tr, time.time() - t0))
+        acc = model.acc.cpu()                                    # the epoch's only host sync
+        dropped = bool(early_stop) and (np.float32(int(acc[2])) / np.float32(max(n_va, 1))) < info.before_val
+        if info.step(step, acc, True, dropped):
             stop = step
             break
-        before_val = acc_val
         result.copy_(model.W_ih)
-    if log:
-        log("    Optimization Finish")
-    out = result.cpu().numpy()
-    if return_info:
-        return out, {"history": hist, "stop_step": stop, "n_train": n_tr, "n_val": n_va, "model": model}
-    return out
+    return result, info.hist, stop
 
 
 def compute_genetovec(pathList, n_genes, hidden_size, learning_rate, max_epoch=500, seed=0, log=print):

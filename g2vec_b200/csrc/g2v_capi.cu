@@ -20,6 +20,10 @@ void set_error(const char *fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static thread_local const int32_t *g_skip = nullptr;
+const int32_t *loop_skip_flag() { return g_skip; }
+void set_loop_skip_flag(const int32_t *p) { g_skip = p; }
+
 int device_props(DeviceProps *out) {
     static thread_local int cached_dev = -1;
     static thread_local DeviceProps cached;

@@ -43,7 +43,8 @@ cbow_rows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
                  int64_t win_begin, int64_t n_win, float inv_n, const float *__restrict__ W_ih,
                  const float *__restrict__ W_ho, float *__restrict__ g_ih, float *__restrict__ g_ho,
                  double *__restrict__ loss_sum, unsigned long long *__restrict__ n_correct,
-                 int32_t reduce_mean) {
+                 int32_t reduce_mean, const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     constexpr int D = 128 * VEC;
     constexpr int D4 = D / 4;
     constexpr int UNR = 8 / VEC;                 // 8 float4 (128 B) in flight per lane
@@ -243,7 +244,9 @@ cbow_rows_generic_kernel(const int32_t *__restrict__ rowptr, const int32_t *__re
                          int64_t win_begin, int64_t n_win, float inv_n, const float *__restrict__ W_ih,
                          const float *__restrict__ W_ho, float *__restrict__ g_ih,
                          float *__restrict__ g_ho, double *__restrict__ loss_sum,
-                         unsigned long long *__restrict__ n_correct, int32_t D, int32_t reduce_mean) {
+                         unsigned long long *__restrict__ n_correct, int32_t D, int32_t reduce_mean,
+                         const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     extern __shared__ float shf[];
     __shared__ CtaAcc sh_acc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -312,7 +315,8 @@ __global__ void __launch_bounds__(256)
 cbow_update_kernel(float *__restrict__ W, float *__restrict__ M, float *__restrict__ Vv,
                    float *__restrict__ G, int64_t n, float *__restrict__ W2, float *__restrict__ M2,
                    float *__restrict__ V2, float *__restrict__ G2, int64_t n2, float alpha_host, float omb1,
-                   float omb2, float eps, const float *__restrict__ alpha_dev) {
+                   float omb2, float eps, const float *__restrict__ alpha_dev, const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     // alpha_dev != NULL: the step size lives on the device (g2v_cbow_adam_tick), so the launch can be replayed
     const float alpha = alpha_dev ? __ldg(alpha_dev + 2) : alpha_host;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -382,7 +386,7 @@ static int launch_rows(const int32_t *rowptr, const int32_t *gene, const uint8_t
                                 : cbow_rows_kernel<VEC, BACKWARD, false, false>);                    \
         if ((rc = rows_grid((const void *)kern, 0, n_win, &grid))) return rc;                        \
         kern<<<grid, kCbowWarps * 32, 0, st>>>(                                                      \
-            rowptr, gene, label, win, win_begin, n_win, inv_n, W_ih, W_ho, g_ih, g_ho, loss_sum, nc, reduce); \
+            rowptr, gene, label, win, win_begin, n_win, inv_n, W_ih, W_ho, g_ih, g_ho, loss_sum, nc, reduce, loop_skip_flag()); \
     }
     if (D == 128) G2V_LAUNCH_VEC(1)
     else if (D == 256) G2V_LAUNCH_VEC(2)
@@ -395,7 +399,7 @@ static int launch_rows(const int32_t *rowptr, const int32_t *gene, const uint8_t
         G2V_CUDA_OK(cudaFuncSetAttribute(cbow_rows_generic_kernel<BACKWARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if ((rc = rows_grid((const void *)cbow_rows_generic_kernel<BACKWARD>, smem, n_win, &grid))) return rc;
         cbow_rows_generic_kernel<BACKWARD><<<grid, kCbowWarps * 32, smem, st>>>(
-            rowptr, gene, label, win, win_begin, n_win, inv_n, W_ih, W_ho, g_ih, g_ho, loss_sum, nc, D, reduce);
+            rowptr, gene, label, win, win_begin, n_win, inv_n, W_ih, W_ho, g_ih, g_ho, loss_sum, nc, D, reduce, loop_skip_flag());
     }
 #undef G2V_LAUNCH_VEC
     G2V_CUDA_OK(cudaGetLastError());
@@ -403,9 +407,86 @@ static int launch_rows(const int32_t *rowptr, const int32_t *gene, const uint8_t
     return 0;
 }
 
+
+// ---- device-side training loop control (G2Vec.py:262-283) ------------------------------------
+// ctl (int64 x 8 in device memory):
+//   [0] stopped      1 once the loop is over: the validation accuracy dropped (strict <, :276) or max_steps ran
+//   [1] step         optimizer steps decided so far
+//   [2] stop_step    step whose validation accuracy dropped, -1 if none (the reference breaks there, :279)
+//   [3] before_val   correct validation windows of the last passed step (before_acc_val, :280; -1 = the -1. of :261)
+//   [4] max_steps    cap on optimizer steps (--epoch)       [5] early_stop   0 = never stop early
+// loop_begin:  if not stopped, copy the weights into `snapshot` (they are the result if THIS step's validation
+//   accuracy drops: the reference returns the W_ih read at :283 after the previous step) and zero the 4 counters.
+// loop_decide: if not stopped, record the step's counters in hist[step][0..3], apply the early-stop rule on the
+//   validation count (same ordering as the float32 ratios the reference compares while n_val < 2^24), advance.
+__global__ void __launch_bounds__(256)
+loop_begin_kernel(const long long *__restrict__ ctl, long long *__restrict__ acc, const float4 *__restrict__ W4,
+                  float4 *__restrict__ S4, int64_t n4, const float *__restrict__ W, float *__restrict__ S, int64_t n) {
+    if (ctl[0] != 0) return;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    if (tid < 4) acc[tid] = 0;
+    if (S == nullptr) return;
+    for (int64_t i = tid; i < n4; i += nth) S4[i] = W4[i];
+    for (int64_t i = (n4 << 2) + tid; i < n; i += nth) S[i] = W[i];
+}
+
+__global__ void loop_decide_kernel(long long *__restrict__ ctl, const long long *__restrict__ acc,
+                                   long long *__restrict__ hist) {
+    if (ctl[0] != 0) return;
+    const long long step = ctl[1];
+    for (int k = 0; k < 4; ++k) hist[step * 4 + k] = acc[k];
+    if (ctl[5] != 0 && acc[2] < ctl[3]) {
+        ctl[0] = 1; ctl[2] = step;                  // dropped: the snapshot taken by loop_begin is the result
+    } else {
+        ctl[3] = acc[2];
+        if (step + 1 >= ctl[4]) ctl[0] = 1;          // ran --epoch steps without a drop
+    }
+    ctl[1] = step + 1;
+}
+
 }  // namespace g2v
 
 using namespace g2v;
+
+extern "C" int g2v_cbow_loop_init(int64_t *ctl, int64_t max_steps, int32_t early_stop, void *stream) {
+    G2V_REQUIRE(ctl && max_steps >= 1, "g2v_cbow_loop_init: bad arguments");
+    const long long h[8] = {0, 0, -1, -1, (long long)max_steps, early_stop ? 1 : 0, 0, 0};
+    G2V_CUDA_OK(cudaMemcpyAsync(ctl, h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    G2V_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));        // h is on this call's stack
+    return 0;
+}
+
+extern "C" int g2v_cbow_loop_attach(const int64_t *ctl) {
+    // the low 32 bits of ctl[0] (little endian) are the `stopped` word every step kernel tests
+    set_loop_skip_flag(reinterpret_cast<const int32_t *>(ctl));
+    return 0;
+}
+
+extern "C" int g2v_cbow_loop_begin(const int64_t *ctl, int64_t *acc, const float *W_ih, float *snapshot, int64_t n,
+                                   void *stream) {
+    G2V_REQUIRE(ctl && acc && n >= 0 && (snapshot == nullptr || W_ih), "g2v_cbow_loop_begin: bad arguments");
+    DeviceProps dp;
+    if (device_props(&dp)) return 1;
+    int64_t blocks = snapshot ? (n / 4 + 255) / 256 : 1;
+    if (blocks > (int64_t)dp.sm_count * 8) blocks = (int64_t)dp.sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    loop_begin_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const long long *>(ctl), reinterpret_cast<long long *>(acc),
+        reinterpret_cast<const float4 *>(W_ih), reinterpret_cast<float4 *>(snapshot), n >> 2, W_ih, snapshot, n);
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int g2v_cbow_loop_decide(int64_t *ctl, const int64_t *acc, int64_t *hist, void *stream) {
+    G2V_REQUIRE(ctl && acc && hist, "g2v_cbow_loop_decide: null pointer");
+    loop_decide_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long *>(ctl),
+                                                          reinterpret_cast<const long long *>(acc),
+                                                          reinterpret_cast<long long *>(hist));
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
 
 extern "C" int g2v_cbow_fwdbwd(const int32_t *rowptr, const int32_t *gene, const uint8_t *label,
                                const int32_t *win, int64_t win_begin, int64_t n_win, float inv_n_total,
@@ -432,7 +513,8 @@ extern "C" int g2v_cbow_eval(const int32_t *rowptr, const int32_t *gene, const u
                               nullptr, n_correct, D, reduce, (cudaStream_t)stream);
 }
 
-__global__ void adam_tick_kernel(float *state, float lr, float beta1, float beta2) {
+__global__ void adam_tick_kernel(float *state, float lr, float beta1, float beta2, const int32_t *skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     // TF1's beta1_power / beta2_power variables, advanced once per optimizer step on the device
     const float b1p = state[0] * beta1, b2p = state[1] * beta2;
     state[0] = b1p; state[1] = b2p;
@@ -441,7 +523,7 @@ __global__ void adam_tick_kernel(float *state, float lr, float beta1, float beta
 
 extern "C" int g2v_cbow_adam_tick(float *state, float lr, float beta1, float beta2, void *stream) {
     G2V_REQUIRE(state != nullptr, "g2v_cbow_adam_tick: null pointer");
-    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2);
+    adam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, lr, beta1, beta2, loop_skip_flag());
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
@@ -470,10 +552,10 @@ extern "C" int g2v_cbow_update(float *W_ih, float *W_ho, float *m_ih, float *v_i
         const float alpha = alpha_dev ? 0.f : lr * sqrtf(1.f - b2p) / (1.f - b1p);
         cbow_update_kernel<G2V_OPT_ADAM_TF1><<<(unsigned)blocks, 256, 0, st>>>(
             W_ih, m_ih, v_ih, g_ih, n, W_ho, m_ho, v_ho, g_ho, (int64_t)D, alpha, 1.f - beta1, 1.f - beta2, eps,
-            alpha_dev);
+            alpha_dev, loop_skip_flag());
     } else {
         cbow_update_kernel<G2V_OPT_SGD><<<(unsigned)blocks, 256, 0, st>>>(
-            W_ih, nullptr, nullptr, g_ih, n, W_ho, nullptr, nullptr, g_ho, (int64_t)D, lr, 0.f, 0.f, 0.f, nullptr);
+            W_ih, nullptr, nullptr, g_ih, n, W_ho, nullptr, nullptr, g_ho, (int64_t)D, lr, 0.f, 0.f, 0.f, nullptr, loop_skip_flag());
     }
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();

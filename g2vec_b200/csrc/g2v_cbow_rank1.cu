@@ -37,7 +37,8 @@ __device__ __forceinline__ void adam1_r1(float &w, float &m, float &v, float g, 
 // ---- s = W_ih . W_ho ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(kR1Warps * 32)
 r1_prepare_kernel(const float *__restrict__ W_ih, const float *__restrict__ W_ho, float *__restrict__ s,
-                  int32_t V, int32_t D) {
+                  int32_t V, int32_t D, const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kR1Warps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kR1Warps;
@@ -71,7 +72,8 @@ r1_windows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict_
                   const uint8_t *__restrict__ label, const int32_t *__restrict__ win, int64_t win_begin,
                   int64_t n_win, float inv_n, const float *__restrict__ s, float *__restrict__ c,
                   double *__restrict__ loss_sum, unsigned long long *__restrict__ n_correct,
-                  int32_t reduce_mean) {
+                  int32_t reduce_mean, const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     constexpr bool BACKWARD = MODE != 0;
     __shared__ R1Acc sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -129,7 +131,9 @@ r1_windows_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict_
 // assignment and shuffle tree => bit-reproducible from run to run (no floating-point atomics).
 __global__ void __launch_bounds__(kR1Warps * 32)
 r1_csc_reduce_kernel(const int32_t *__restrict__ cscptr, const int32_t *__restrict__ csc_pos,
-                     const float *__restrict__ dO, float *__restrict__ c, int32_t V) {
+                     const float *__restrict__ dO, float *__restrict__ c, int32_t V,
+                     const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kR1Warps + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * kR1Warps;
@@ -155,7 +159,8 @@ __global__ void __launch_bounds__(kR1Warps * 32)
 r1_update_kernel(float *__restrict__ W_ih, float *__restrict__ M, float *__restrict__ Vv,
                  const float *__restrict__ W_ho, float *__restrict__ c, float *__restrict__ g_part, int32_t V,
                  int32_t D, float alpha_host, float omb1, float omb2, float eps,
-                 const float *__restrict__ alpha_dev) {
+                 const float *__restrict__ alpha_dev, const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     const float alpha = alpha_dev ? __ldg(alpha_dev + 2) : alpha_host;
     // g_ho = W_ih^T . c is reduced WITHOUT atomics so that the step is bit-reproducible: every warp owns a
     // row of sh_gho, the block sums its rows in warp order into g_part[blockIdx.x][:], and
@@ -238,7 +243,8 @@ template <int OPT>
 __global__ void __launch_bounds__(1024)
 r1_update_ho_kernel(float *__restrict__ W_ho, float *__restrict__ m, float *__restrict__ v,
                     const float *__restrict__ g_part, int32_t n_part, int32_t D, float alpha_host, float omb1,
-                    float omb2, float eps, const float *__restrict__ alpha_dev) {
+                    float omb2, float eps, const float *__restrict__ alpha_dev, const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     const float alpha = alpha_dev ? __ldg(alpha_dev + 2) : alpha_host;
     __shared__ float sh[32][33];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -287,7 +293,7 @@ extern "C" int g2v_cbow_r1_prepare(const float *W_ih, const float *W_ho, float *
     G2V_REQUIRE(V > 0 && D > 0 && W_ih && W_ho && s, "g2v_cbow_r1_prepare: bad arguments");
     int grid = 0, rc;
     if ((rc = r1_grid((const void *)r1_prepare_kernel, 0, V, &grid))) return rc;
-    r1_prepare_kernel<<<grid, kR1Warps * 32, 0, (cudaStream_t)stream>>>(W_ih, W_ho, s, V, D);
+    r1_prepare_kernel<<<grid, kR1Warps * 32, 0, (cudaStream_t)stream>>>(W_ih, W_ho, s, V, D, loop_skip_flag());
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
@@ -307,11 +313,11 @@ extern "C" int g2v_cbow_r1_windows(const int32_t *rowptr, const int32_t *gene, c
     if (c) {
         if ((rc = r1_grid((const void *)r1_windows_kernel<1>, 0, (n_win + 3) / 4, &grid))) return rc;
         r1_windows_kernel<1><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, win_begin, n_win,
-                                                            inv_n_total, s, c, loss_sum, nc, reduce);
+                                                            inv_n_total, s, c, loss_sum, nc, reduce, loop_skip_flag());
     } else {
         if ((rc = r1_grid((const void *)r1_windows_kernel<0>, 0, (n_win + 3) / 4, &grid))) return rc;
         r1_windows_kernel<0><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, win_begin, n_win, 0.f,
-                                                            s, nullptr, nullptr, nc, reduce);
+                                                            s, nullptr, nullptr, nc, reduce, loop_skip_flag());
     }
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
@@ -332,10 +338,10 @@ extern "C" int g2v_cbow_r1_windows_csc(const int32_t *rowptr, const int32_t *gen
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = r1_grid((const void *)r1_windows_kernel<2>, 0, (n_win + 3) / 4, &grid))) return rc;
     r1_windows_kernel<2><<<grid, kR1Warps * 32, 0, st>>>(rowptr, gene, label, win, 0, n_win, inv_n_total, s, dO,
-                                                        loss_sum, nc, reduce);
+                                                        loss_sum, nc, reduce, loop_skip_flag());
     G2V_CUDA_OK(cudaGetLastError());
     if ((rc = r1_grid((const void *)r1_csc_reduce_kernel, 0, V, &grid))) return rc;
-    r1_csc_reduce_kernel<<<grid, kR1Warps * 32, 0, st>>>(cscptr, csc_pos, dO, c, V);
+    r1_csc_reduce_kernel<<<grid, kR1Warps * 32, 0, st>>>(cscptr, csc_pos, dO, c, V, loop_skip_flag());
     G2V_CUDA_OK(cudaGetLastError());
     count_launch(2);
     return 0;
@@ -357,7 +363,7 @@ static int launch_r1_update(float *W_ih, float *M, float *Vv, const float *W_ho,
     if ((rc = r1_grid((const void *)r1_update_kernel<VEC, OPT>, smem, V, &grid))) return rc;
     if (grid > kR1MaxParts) grid = kR1MaxParts;
     r1_update_kernel<VEC, OPT><<<grid, kR1Warps * 32, smem, st>>>(W_ih, M, Vv, W_ho, c, g_ho, V, D, alpha, omb1, omb2, eps,
-                                                                  alpha_dev);
+                                                                  alpha_dev, loop_skip_flag());
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
     *grid_out = grid;
@@ -395,9 +401,9 @@ extern "C" int g2v_cbow_r1_update(float *W_ih, float *W_ho, float *m_ih, float *
 #undef G2V_R1
     if (rc) return rc;
     if (optimizer == G2V_OPT_ADAM_TF1)
-        r1_update_ho_kernel<G2V_OPT_ADAM_TF1><<<(D + 31) / 32, 1024, 0, st>>>(W_ho, m_ho, v_ho, g_ho, parts, D, alpha, omb1, omb2, eps, alpha_dev);
+        r1_update_ho_kernel<G2V_OPT_ADAM_TF1><<<(D + 31) / 32, 1024, 0, st>>>(W_ho, m_ho, v_ho, g_ho, parts, D, alpha, omb1, omb2, eps, alpha_dev, loop_skip_flag());
     else
-        r1_update_ho_kernel<G2V_OPT_SGD><<<(D + 31) / 32, 1024, 0, st>>>(W_ho, nullptr, nullptr, g_ho, parts, D, alpha, omb1, omb2, eps, nullptr);
+        r1_update_ho_kernel<G2V_OPT_SGD><<<(D + 31) / 32, 1024, 0, st>>>(W_ho, nullptr, nullptr, g_ho, parts, D, alpha, omb1, omb2, eps, nullptr, loop_skip_flag());
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
     return g2v_cbow_r1_prepare(W_ih, W_ho, s, V, D, stream);

@@ -30,6 +30,8 @@
 
 namespace g2v {
 
+constexpr bool kDefaultSlabScatterTma = false;   // set from the B200 measurement in profiles/r2
+
 __device__ __forceinline__ float4 ld_stream4(const float4 *p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream4(float4 *p, float4 v) { __stcs(p, v); }
 
@@ -65,7 +67,9 @@ cbow_slab_fwd_kernel(const int32_t *__restrict__ gene, const uint8_t *__restrict
                      const int32_t *__restrict__ slabptr, int32_t S1, int32_t s_lo, int32_t s_hi, float inv_n,
                      const float *__restrict__ W_ih, const float *__restrict__ W_ho, float *__restrict__ hbuf,
                      float *__restrict__ obuf, float *__restrict__ dOut, float *__restrict__ g_ho,
-                     double *__restrict__ loss_sum, unsigned long long *__restrict__ n_correct, int32_t reduce_mean) {
+                     double *__restrict__ loss_sum, unsigned long long *__restrict__ n_correct, int32_t reduce_mean,
+                     const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     constexpr int D = 128 * VEC;
     constexpr int D4 = D / 4;
     constexpr int UNR = 8 / VEC;                 // 8 float4 (128 B) in flight per lane
@@ -174,17 +178,27 @@ cbow_slab_fwd_kernel(const int32_t *__restrict__ gene, const uint8_t *__restrict
     }
 }
 
-template <int VEC>
+// TMA = false: every lane adds its 16 bytes of the gradient row with red.global.add.v4.f32 (LSU/L1TEX path:
+// VEC warp-wide RED.128 per gene row).  TMA = true: the row dO*W_ho -- the same for every gene of the
+// window -- is staged once in shared memory and added into g_ih[gene,:] with ONE bulk reduction per gene
+// (cp.reduce.async.bulk.global.shared::cta.add.f32, D*4 bytes, SASS UBLKRED) issued by one lane: the scatter
+// leaves the LSU/L1TEX path, which is what bounds the L2-resident backward passes (ncu: l1tex 87 %).
+// Two staging rows per warp, so that a window's row can be written while the previous window's bulk
+// reductions are still reading theirs.
+template <int VEC, bool TMA>
 __global__ void __launch_bounds__(kCbowWarps * 32)
 cbow_slab_bwd_kernel(const int32_t *__restrict__ gene, int64_t n_win, const int32_t *__restrict__ slabptr, int32_t S1,
                      int32_t s, const float *__restrict__ dOut, const float *__restrict__ W_ho,
-                     float *__restrict__ g_ih) {
+                     float *__restrict__ g_ih, const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
     constexpr int D = 128 * VEC;
+    __shared__ __align__(128) float sh_row[TMA ? kCbowWarps * 2 * D : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 who[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) who[v] = ldg4(reinterpret_cast<const float4 *>(W_ho) + v * 32 + lane);
     const int64_t warps_total = (int64_t)gridDim.x * kCbowWarps;
+    int stage = 0;
     for (int64_t i = (int64_t)blockIdx.x * kCbowWarps + warp; i < n_win; i += warps_total) {
         const int32_t b = __ldg(slabptr + i * S1 + s), e = __ldg(slabptr + i * S1 + s + 1);
         if (b == e) continue;
@@ -192,17 +206,38 @@ cbow_slab_bwd_kernel(const int32_t *__restrict__ gene, int64_t n_win, const int3
         float4 gv[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) gv[v] = make_float4(who[v].x * hs, who[v].y * hs, who[v].z * hs, who[v].w * hs);
-        for (int32_t base = b; base < e; base += 32) {
-            const int cnt = min(32, e - base);
-            const int32_t g = (lane < cnt) ? __ldg(gene + base + lane) : 0;
-            for (int k = 0; k < cnt; ++k) {
-                const int32_t gk = __shfl_sync(0xffffffffu, g, k);
-                float *dst = g_ih + (size_t)gk * D + lane * 4;
+        if (TMA) {
+            float *row = sh_row + (size_t)(warp * 2 + stage) * D;
+            // at most one older group (the other stage) may still be reading shared memory
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) red_add4(dst + v * 128, gv[v]);
+            for (int v = 0; v < VEC; ++v) reinterpret_cast<float4 *>(row)[v * 32 + lane] = gv[v];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+            __syncwarp();
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(row);
+            for (int32_t j = b + lane; j < e; j += 32) {
+                float *dst = g_ih + (size_t)__ldg(gene + j) * D;
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                             ::"l"(dst), "r"(src), "n"(D * 4)
+                             : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            stage ^= 1;
+        } else {
+            for (int32_t base = b; base < e; base += 32) {
+                const int cnt = min(32, e - base);
+                const int32_t g = (lane < cnt) ? __ldg(gene + base + lane) : 0;
+                for (int k = 0; k < cnt; ++k) {
+                    const int32_t gk = __shfl_sync(0xffffffffu, g, k);
+                    float *dst = g_ih + (size_t)gk * D + lane * 4;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) red_add4(dst + v * 128, gv[v]);
+                }
             }
         }
     }
+    if (TMA) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 struct SlabLayout {            // carving of the caller's workspace
@@ -245,7 +280,7 @@ static int launch_fwd_passes(const int32_t *gene, const uint8_t *label, const in
         auto kern = cbow_slab_fwd_kernel<VEC, MODE, F, L>;                                                 \
         if ((rc = rows_grid((const void *)kern, 0, n_win, &grid))) return rc;                              \
         kern<<<grid, kCbowWarps * 32, 0, st>>>(gene, label, win, win_begin, n_win, l.slabptr, S + 1, lo, hi, inv_n, \
-                                               W_ih, W_ho, l.hbuf, l.obuf, l.dO, g_ho, loss_sum, nc, reduce); \
+                                               W_ih, W_ho, l.hbuf, l.obuf, l.dO, g_ho, loss_sum, nc, reduce, loop_skip_flag()); \
     }
         if (first && last) G2V_SLAB_FWD(true, true)
         else if (first) G2V_SLAB_FWD(true, false)
@@ -261,10 +296,13 @@ static int launch_fwd_passes(const int32_t *gene, const uint8_t *label, const in
 template <int VEC>
 static int launch_bwd_passes(const int32_t *gene, int64_t n_win, const SlabLayout &l, int32_t S, const float *W_ho,
                              float *g_ih, cudaStream_t st) {
+    const char *sc = getenv("G2V_CBOW_SLAB_SCATTER");             // "tma" (default) / "red": A/B hook, see profiles/r2
+    const bool tma = sc ? sc[0] == 't' : kDefaultSlabScatterTma;
+    auto kern = tma ? cbow_slab_bwd_kernel<VEC, true> : cbow_slab_bwd_kernel<VEC, false>;
     int grid = 0, rc;
-    if ((rc = rows_grid((const void *)cbow_slab_bwd_kernel<VEC>, 0, n_win, &grid))) return rc;
+    if ((rc = rows_grid((const void *)kern, 0, n_win, &grid))) return rc;
     for (int s = 0; s < S; ++s) {
-        cbow_slab_bwd_kernel<VEC><<<grid, kCbowWarps * 32, 0, st>>>(gene, n_win, l.slabptr, S + 1, s, l.dO, W_ho, g_ih);
+        kern<<<grid, kCbowWarps * 32, 0, st>>>(gene, n_win, l.slabptr, S + 1, s, l.dO, W_ho, g_ih, loop_skip_flag());
         G2V_CUDA_OK(cudaGetLastError());
         count_launch();
     }

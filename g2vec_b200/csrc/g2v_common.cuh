@@ -30,6 +30,14 @@ void count_launch(int n = 1);
         }                               \
     } while (0)
 
+// Device-side loop control (g2v_cbow_loop_*): when a training loop is driven from a CUDA graph, every kernel of a
+// step takes the address of the loop's `stopped` word and returns at once if it is set, so that the steps that
+// follow the early stop (G2Vec.py:276-279) inside an already enqueued graph are no-ops.
+void set_loop_skip_flag(const int32_t *p);
+const int32_t *loop_skip_flag();   // thread-local, set by g2v_cbow_loop_attach (NULL = no loop control)
+#define G2V_SKIP_IF_STOPPED(skip) \
+    do { if ((skip) != nullptr && *reinterpret_cast<const volatile int32_t *>(skip) != 0) return; } while (0)
+
 struct DeviceProps {
     int sm_count;
     int cc_major, cc_minor;

@@ -139,6 +139,25 @@ int g2v_cbow_eval(const int32_t *rowptr, const int32_t *gene, const uint8_t *lab
                   void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Device-side control of the training loop (G2Vec.py:262-283), so that several iterations of
+ * the reference's loop can be enqueued -- or replayed as ONE CUDA graph -- without a host decision in between.
+ *   ctl  [8] int64 in device memory: {stopped, step, stop_step, before_val, max_steps, early_stop, -, -}
+ *        g2v_cbow_loop_init sets {0, 0, -1, -1, max_steps, early_stop}.
+ *   g2v_cbow_loop_attach(ctl): from now on every CBOW kernel launched by THIS host thread first reads
+ *        ctl.stopped and returns at once if it is set (attach(NULL) detaches).
+ *   g2v_cbow_loop_begin: unless stopped, copies W_ih [n floats] into `snapshot` (nullable) -- the weights the
+ *        reference would return if this step's validation accuracy drops (:283,:286) -- and zeroes acc[0..3].
+ *   g2v_cbow_loop_decide: unless stopped, stores acc[0..3] (loss-sum bits, pre-update train correct, validation
+ *        correct, train correct) in hist[step*4 ..], applies `if acc_val < before_acc_val: break` (:276) on the
+ *        validation count, else before_val = count (:280); stops after max_steps; step += 1.
+ * The host reads ctl / hist whenever it wants to print (every 5th step, :269) instead of after every step.
+ * ------------------------------------------------------------------------------------- */
+int g2v_cbow_loop_init(int64_t *ctl, int64_t max_steps, int32_t early_stop, void *stream);
+int g2v_cbow_loop_attach(const int64_t *ctl);
+int g2v_cbow_loop_begin(const int64_t *ctl, int64_t *acc, const float *W_ih, float *snapshot, int64_t n, void *stream);
+int g2v_cbow_loop_decide(int64_t *ctl, const int64_t *acc, int64_t *hist, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * HOT PATH 2 for tables larger than the L2 (csrc/g2v_cbow_slab.cu): the same step as g2v_cbow_fwdbwd /
  * g2v_cbow_eval, processed gene slab by gene slab so that the gathered rows and the gradient rows stay
  * L2-resident.  Needs windows whose gene lists are strictly ascending (tuple(sorted(path)), G2Vec.py:345).

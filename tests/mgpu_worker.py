@@ -25,13 +25,16 @@ def main(out):
     # CBOW: 5 steps on the oracle-made ex_* windows
     (rowptr, gene, label), _ = helpers.ex_windows(reps=2)
     W0, Wo0 = helpers.init_weights(7523, 128, 0)
-    got, info = g2v.train_cbow(rowptr, gene, label, 7523, 128, 0.005, max_epoch=5, seed=0, W_ih0=W0, W_ho0=Wo0,
+    # 11 steps: step 0 eagerly, then two 5-step chunks -- on N GPUs each chunk is ONE CUDA graph that contains the
+    # NCCL all-reduces (g2vec_b200.cbow._device_loop)
+    got, info = g2v.train_cbow(rowptr, gene, label, 7523, 128, 0.005, max_epoch=11, seed=0, W_ih0=W0, W_ho0=Wo0,
                                early_stop=False, log=None, return_info=True)
     if rank == 0:
         full = np.empty((2 * 7523, 80), np.int32); fl = np.empty(2 * 7523, np.int32)
         for r in range(world):
             full[r::world], fl[r::world] = gathered[r]
-        np.savez(out, W=got, hist=np.array(info["history"], dtype=np.float64), nodes=full, lens=fl)
+        np.savez(out, W=got, hist=np.array(info["history"], dtype=np.float64), nodes=full, lens=fl,
+                 graph=np.array(info["graph"]))
     dist.destroy_process_group()
 
 

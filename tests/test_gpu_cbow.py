@@ -390,6 +390,27 @@ def test_graph_replayed_steps_equal_eager_steps(g2v, algo):
     assert h[0] == b1p and h[1] == b2p and abs(h[2] - alpha) <= 1e-9
 
 
+@pytest.mark.parametrize("algo", ["rows", "rank1"])
+def test_device_loop_early_stop_equals_host_driven_steps(g2v, algo):
+    """The early stop decided on the device inside a 5-step CUDA graph (iterations after the drop are no-ops,
+    the snapshot is the weights before the dropping step) against the same launches run eagerly."""
+    g = helpers.cbow_golden("cbow_small.npz")
+    kw = dict(max_epoch=500, seed=g["seed"], log=None, algo=algo, return_info=True)
+    a, ia = g2v.train_cbow(g["rowptr"], g["gene"], g["label"], g["V"], g["D"], g["lr"], use_graph=True, **kw)
+    b, ib = g2v.train_cbow(g["rowptr"], g["gene"], g["label"], g["V"], g["D"], g["lr"], use_graph=False, **kw)
+    assert ia["graph"] and not ib["graph"]
+    assert ia["stop_step"] == ib["stop_step"] == g["stop_step"] and g["stop_step"] % 5 not in (0,)   # mid-chunk stop
+    assert len(ia["history"]) == len(ib["history"]) == g["stop_step"] + 1
+    assert rel_max(a, b) < 1e-5 and rel_max(a, g["W_ref"]) < RTOL_VEC
+    # --epoch below the stop step: the cap ends the loop, the result is the final weights
+    c, ic = g2v.train_cbow(g["rowptr"], g["gene"], g["label"], g["V"], g["D"], g["lr"], use_graph=True,
+                           **dict(kw, max_epoch=7))
+    assert ic["stop_step"] is None and len(ic["history"]) == 7 and all(h[2] is not None for h in ic["history"])
+    want, _, _, _ = oracle.cbow_train(g["rowptr"], g["gene"], g["label"], g["tr"], g["va"], g["W0"], g["Wo0"], g["lr"],
+                                      max_steps=7, early_stop=False)
+    assert rel_max(c, want) < RTOL_VEC
+
+
 def test_window_feeder_double_buffered_uploads(g2v):
     """Feeding the windows from pinned host memory (int16 gene ids on the wire, two device buffer sets)
     gives the same step results as resident windows."""
@@ -462,9 +483,8 @@ def test_slab_passes_equal_oracle_and_fused_kernel(g2v, monkeypatch, D, reduce, 
     single-pass kernel; windows that have no gene in a slab, empty windows and a window list with an offset."""
     import torch
     V, N = 700, 2500
-    rowptr, gene, label = helpers.random_windows(N, V, 1, 60, seed=D + slabs)
-    rowptr[7] = rowptr[6]                                          # an empty window
-    gene = gene[:rowptr[N - 1]].copy(); rowptr[N] = rowptr[N - 1]  # and an empty last one
+    rowptr, gene, label = helpers.random_windows(N, V, 0, 60, seed=D + slabs)     # lengths 0..60: empty windows too
+    assert (np.diff(rowptr) == 0).sum() > 5
     W0, Wo0 = helpers.init_weights(V, D, 5)
     rs = np.random.RandomState(1)
     win = rs.permutation(N)[:2000].astype(np.int64)

@@ -34,8 +34,10 @@ def test_two_gpus_equal_one_gpu(tmp_path):
     N = len(rowptr) - 1
     tr, va = oracle.split_indices(N, 0)
     W0, Wo0 = helpers.init_weights(7523, 128, 0)
-    ref, hist, _, _ = oracle.cbow_train(rowptr, gene, label, tr, va, W0, Wo0, 0.005, max_steps=5, early_stop=False)
+    ref, hist, _, _ = oracle.cbow_train(rowptr, gene, label, tr, va, W0, Wo0, 0.005, max_steps=11, early_stop=False)
     assert np.abs(z["W"] - ref).max() < 1e-4 * np.abs(ref).max()
+    print("multi-GPU chunks ran as CUDA graphs with NCCL inside:", bool(z["graph"]))
+    assert len(z["hist"]) == 11
     for (s_, av, at), row in zip(hist, z["hist"]):
         assert abs(av - row[1]) <= 2.0 / len(va) + 1e-7 and abs(at - row[2]) <= 2.0 / len(tr) + 1e-7
 
