@@ -56,6 +56,7 @@ SIGNATURES = {
     "g2v_pcc_edge_weights": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _vp, _vp]),
     "g2v_paths_canonicalise": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "g2v_paths_mark": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "g2v_test_l2_rows": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "g2v_test_draws": (ctypes.c_int, [_u64, _u64, _i32, _vp, _vp]),
     "g2v_test_curand_draws": (ctypes.c_int, [_u64, _u64, _i32, _vp, _vp]),
 }
@@ -87,7 +88,7 @@ def load():
         fn = getattr(lib, name)        # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.g2v_abi_version() != 1:
+    if lib.g2v_abi_version() != 2:
         raise RuntimeError("libg2vec_b200.so ABI version mismatch")
     _lib = lib
     return lib

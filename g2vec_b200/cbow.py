@@ -88,8 +88,10 @@ class CbowModel:
             raise ValueError("algo must be 'rows' (gather/scatter of embedding rows) or 'rank1' (collapsed)")
         self.algo = algo
         if algo == "rows":
-            self.g_ho = z(self.D)
-            self.g_ih = z(self.V, self.D)
+            # one allocation [g_ih | g_ho]: a multi-GPU step all-reduces the whole gradient with ONE collective
+            self.g_flat = z(self.V * self.D + self.D)
+            self.g_ih = self.g_flat[:self.V * self.D].view(self.V, self.D)
+            self.g_ho = self.g_flat[self.V * self.D:]
             self.s = self.c = None
         else:                       # rank-1: s = W_ih.W_ho, c = X^T.dO; no dense gradient
             self.g_ih = None
@@ -157,7 +159,7 @@ class CbowModel:
 
     def grad_tensors(self):
         """What a multi-GPU step must all-reduce (sum) between fwdbwd() and update()."""
-        return [self.g_ih, self.g_ho] if self.algo == "rows" else [self.c]
+        return [self.g_flat] if self.algo == "rows" else [self.c]
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -246,33 +248,6 @@ class CbowModel:
                                     self.W_ho.data_ptr(), self.acc.data_ptr() + 8 * slot, self.V, self.D,
                                     self.reduce, self._stream())
         _capi.check(rc, "g2v_cbow_eval")
-
-    def make_step(self, tr_d, n_tr, va_d, acc_pin, with_train_eval, use_graph=True):
-        """One iteration of the reference loop (G2Vec.py:262-267) on ONE GPU as a replayable callable:
-        zero counters, fwd+bwd, optimizer, validation accuracy, optionally training accuracy, counters ->
-        pinned host memory.  With use_graph the launches are captured once into a CUDA graph."""
-        def body():
-            self.acc.zero_()
-            if tr_d.shape[0]:
-                self.fwdbwd(tr_d, n_tr)
-            self.update()
-            if va_d.shape[0]:
-                self.evaluate(va_d, 2)
-            if with_train_eval and tr_d.shape[0]:
-                self.evaluate(tr_d, 3)
-            acc_pin.copy_(self.acc, non_blocking=True)
-        if not use_graph:
-            return body
-        g = torch.cuda.CUDAGraph()
-        t_before = self.t
-        with torch.cuda.graph(g):
-            body()
-        self.t = t_before                    # capture records, it does not execute
-
-        def replay():
-            self.t += 1
-            g.replay()
-        return replay
 
     def loss_sum(self, acc_host):
         return float(acc_host[:1].view(torch.float64)[0])
@@ -426,6 +401,78 @@ class _LoopLog:
         return False
 
 
+class DeviceLoop:
+    """One model's training loop state on the device (g2v_cbow_loop_*) and the launches of one iteration of the
+    reference loop (G2Vec.py:262-267): snapshot + zero counters, fwd+bwd, [all-reduce], optimizer, validation
+    accuracy, [training accuracy], [all-reduce of the counters], decide.  Used by train_cbow and by bench.py."""
+
+    def __init__(self, model, dist, tr_d, va_d, n_tr, max_epoch, early_stop):
+        self.m, self.dist, self.tr_d, self.va_d, self.n_tr = model, dist, tr_d, va_d, n_tr
+        self.n_tr_loc, self.n_va_loc = int(tr_d.shape[0]), int(va_d.shape[0])
+        dev = model.device
+        self.ctl = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.hist_d = torch.zeros(max(max_epoch, 1) * 4, dtype=torch.int64, device=dev)
+        self.ctl_pin = torch.zeros(8, dtype=torch.int64).pin_memory()
+        self.hist_pin = torch.zeros(max(max_epoch, 1) * 4, dtype=torch.int64).pin_memory()
+        self.result = model.W_ih.clone()         # snapshot buffer: W_ih before the step being decided
+        self.max_epoch, self.early_stop = int(max_epoch), bool(early_stop)
+        self.reset()
+
+    def _st(self):
+        return torch.cuda.current_stream(self.m.device).cuda_stream
+
+    def reset(self):
+        _capi.check(self.m.lib.g2v_cbow_loop_init(self.ctl.data_ptr(), self.max_epoch, int(self.early_stop), self._st()),
+                    "g2v_cbow_loop_init")
+
+    def attach(self):
+        _capi.check(self.m.lib.g2v_cbow_loop_attach(self.ctl.data_ptr()), "g2v_cbow_loop_attach")
+
+    def detach(self):
+        _capi.check(self.m.lib.g2v_cbow_loop_attach(None), "g2v_cbow_loop_attach")
+
+    def one(self, show, m_fb=None, m_upd=None, m_val=None):
+        """Enqueue one iteration (the optional events mark the end of fwd+bwd, of the update, of the validation pass)."""
+        m, lib, dist = self.m, self.m.lib, self.dist
+        _capi.check(lib.g2v_cbow_loop_begin(self.ctl.data_ptr(), m.acc.data_ptr(), m.W_ih.data_ptr(),
+                                            self.result.data_ptr(), m.V * m.D, self._st()), "g2v_cbow_loop_begin")
+        if self.n_tr_loc:
+            m.fwdbwd(self.tr_d, self.n_tr)       # acc[1] += correct predictions with the PRE-update weights
+        if m_fb is not None:
+            m_fb.record()
+        if dist:
+            for g in m.grad_tensors():
+                dist.all_reduce(g)               # rows: ONE collective over [g_ih | g_ho]; rank1: c
+        m.update()
+        if m_upd is not None:
+            m_upd.record()
+        if self.n_va_loc:
+            m.evaluate(self.va_d, 2)
+        if m_val is not None:
+            m_val.record()
+        if show and self.n_tr_loc:
+            m.evaluate(self.tr_d, 3)
+        if dist:
+            dist.all_reduce(m.acc[1:4])
+        _capi.check(lib.g2v_cbow_loop_decide(self.ctl.data_ptr(), m.acc.data_ptr(), self.hist_d.data_ptr(), self._st()),
+                    "g2v_cbow_loop_decide")
+
+    def fetch(self):
+        self.ctl_pin.copy_(self.ctl, non_blocking=True)
+        self.hist_pin.copy_(self.hist_d, non_blocking=True)
+
+    def capture(self, pattern):
+        """The iterations of `pattern` (list of show flags) + the status read-back as one CUDA graph."""
+        g = torch.cuda.CUDAGraph()
+        t_before = self.m.t
+        with torch.cuda.graph(g):
+            for sh in pattern:
+                self.one(sh)
+            self.fetch()
+        self.m.t = t_before                      # capture records, it does not execute
+        return g
+
+
 def _device_loop(model, dist, tr_d, va_d, n_tr, n_va, n_tr_loc, n_va_loc, max_epoch, early_stop, log, eval_train,
                  use_graph, chunk=5):
     """Full-batch loop of G2Vec.py:262-283 with the early-stop rule, the result snapshot and the step counter on
@@ -434,84 +481,50 @@ def _device_loop(model, dist, tr_d, va_d, n_tr, n_va, n_tr_loc, n_va_loc, max_ep
     instead of once per step.  Iterations enqueued after the stop are no-ops (every kernel tests ctl.stopped).
     Multi-GPU: the all-reduces are part of the captured graph (NCCL is capturable); if capture is refused the
     same launches run eagerly."""
-    lib, dev = model.lib, model.device
-    st = lambda: torch.cuda.current_stream(dev).cuda_stream
-    ctl = torch.zeros(8, dtype=torch.int64, device=dev)
-    hist_d = torch.zeros(max(max_epoch, 1) * 4, dtype=torch.int64, device=dev)
-    ctl_pin = torch.zeros(8, dtype=torch.int64).pin_memory()
-    hist_pin = torch.zeros(max(max_epoch, 1) * 4, dtype=torch.int64).pin_memory()
-    _capi.check(lib.g2v_cbow_loop_init(ctl.data_ptr(), int(max_epoch), int(bool(early_stop)), st()), "g2v_cbow_loop_init")
-    result = model.W_ih.clone()                  # snapshot buffer: W_ih before the step being decided
+    dev = model.device
+    loop = DeviceLoop(model, dist, tr_d, va_d, n_tr, max_epoch, early_stop)
     shown = lambda s: s % 5 == 0 or eval_train == "always"
     info = _LoopLog(n_tr, n_va, log)
 
-    def one(show):
-        _capi.check(lib.g2v_cbow_loop_begin(ctl.data_ptr(), model.acc.data_ptr(), model.W_ih.data_ptr(),
-                                            result.data_ptr(), model.V * model.D, st()), "g2v_cbow_loop_begin")
-        if n_tr_loc:
-            model.fwdbwd(tr_d, n_tr)             # acc[1] += correct predictions with the PRE-update weights
-        if dist:
-            for g in model.grad_tensors():
-                dist.all_reduce(g)
-        model.update()
-        if n_va_loc:
-            model.evaluate(va_d, 2)
-        if show and n_tr_loc:
-            model.evaluate(tr_d, 3)
-        if dist:
-            dist.all_reduce(model.acc[1:4])
-        _capi.check(lib.g2v_cbow_loop_decide(ctl.data_ptr(), model.acc.data_ptr(), hist_d.data_ptr(), st()),
-                    "g2v_cbow_loop_decide")
-
-    def fetch():
-        ctl_pin.copy_(ctl, non_blocking=True)
-        hist_pin.copy_(hist_d, non_blocking=True)
-
     def consume(lo, hi):
         """Host view of steps lo..hi-1 after a sync; True when the loop is over."""
-        decided, stop_step = int(ctl_pin[1]), int(ctl_pin[2])
+        decided, stop_step = int(loop.ctl_pin[1]), int(loop.ctl_pin[2])
         for s in range(lo, min(hi, decided)):
-            if info.step(s, hist_pin[4 * s:4 * s + 4], shown(s), s == stop_step):
+            if info.step(s, loop.hist_pin[4 * s:4 * s + 4], shown(s), s == stop_step):
                 return True
-        return bool(int(ctl_pin[0]))
+        return bool(int(loop.ctl_pin[0]))
 
-    _capi.check(lib.g2v_cbow_loop_attach(ctl.data_ptr()), "g2v_cbow_loop_attach")
+    loop.attach()
+    graph = None
     try:
-        one(True); fetch()                       # step 0 eagerly: it also warms every kernel up before a capture
+        loop.one(True); loop.fetch()             # step 0 eagerly: it also warms every kernel up before a capture
         torch.cuda.current_stream(dev).synchronize()
         done, over = 1, consume(0, 1)
-        graph, graph_failed = None, not use_graph
+        graph_failed, graph_pattern = not use_graph, None
         while not over and done < max_epoch:
             k = min(chunk, max_epoch - done)
             pattern = [shown(done + i) for i in range(k)]
             if k == chunk and not graph_failed and graph is None:
                 try:
-                    g = torch.cuda.CUDAGraph()
-                    t_before = model.t
-                    with torch.cuda.graph(g):
-                        for sh in pattern:
-                            one(sh)
-                        fetch()
-                    model.t = t_before           # capture records, it does not execute
-                    graph, graph_pattern = g, pattern
+                    graph, graph_pattern = loop.capture(pattern), pattern
                 except Exception:
                     if dist is None:
                         raise
                     graph_failed = True          # collectives not capturable here: same launches, eagerly
-            if graph is not None and k == chunk and pattern == graph_pattern:
+            if graph is not None and pattern == graph_pattern:
                 model.t += k
                 graph.replay()
             else:
                 for sh in pattern:
-                    one(sh)
-                fetch()
+                    loop.one(sh)
+                loop.fetch()
             torch.cuda.current_stream(dev).synchronize()        # one host sync per `chunk` steps
             over = consume(done, done + k)
             done += k
-        stop = int(ctl_pin[2]) if int(ctl_pin[2]) >= 0 else None
+        stop = int(loop.ctl_pin[2]) if int(loop.ctl_pin[2]) >= 0 else None
         if stop is None and info.hist and info.hist[-1][2] is None:
             # ACC[tr] of the last step was never needed for a log line; evaluate it once for the history
-            _capi.check(lib.g2v_cbow_loop_attach(None), "g2v_cbow_loop_attach")
+            loop.detach()
             model.acc.zero_()
             if n_tr_loc:
                 model.evaluate(tr_d, 3)
@@ -521,10 +534,10 @@ def _device_loop(model, dist, tr_d, va_d, n_tr, n_va, n_tr_loc, n_va_loc, max_ep
             last = info.hist[-1]
             info.hist[-1] = (last[0], last[1], float(np.float32(int(a[3])) / np.float32(max(n_tr, 1))))
     finally:
-        _capi.check(lib.g2v_cbow_loop_attach(None), "g2v_cbow_loop_attach")
-    # stopped early: the snapshot taken before the dropping step (G2Vec.py:283,286); else the final weights
+        loop.detach()
     model.loop_used_graph = graph is not None
-    return (result if stop is not None else model.W_ih), info.hist, stop
+    # stopped early: the snapshot taken before the dropping step (G2Vec.py:283,286); else the final weights
+    return (loop.result if stop is not None else model.W_ih), info.hist, stop
 
 
 def _minibatch_loop(model, dist, world, tr_d, va_d, n_tr, n_va, n_tr_loc, n_va_loc, max_epoch, early_stop, log, batch):

@@ -62,9 +62,62 @@ __global__ void curand_draws_kernel(uint64_t seed, uint64_t subseq, int32_t n, u
     }
 }
 
+// Measurement hook (bench.py): the rate at which one warp per 32 row ids can (mode 0) read rows of a [V, D]
+// float table with one LDG.128 per lane per 512 bytes, or (mode 1) add a constant row into them with
+// red.global.add.v4.f32 -- the two memory operations of the CBOW kernels with the arithmetic removed.  On a table
+// that fits the L2 this is the L2 / L1TEX ceiling the fused kernel is compared with.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+l2_rows_kernel(const float *__restrict__ table, float *__restrict__ grad, const int32_t *__restrict__ idx, int64_t n_idx,
+               int32_t VEC, float *__restrict__ sink) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+    const int D4 = VEC * 32;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 one = make_float4(1e-9f, 1e-9f, 1e-9f, 1e-9f);
+    for (int64_t base = warp * 32; base < n_idx; base += nwarps * 32) {
+        const int cnt = (int)min((int64_t)32, n_idx - base);
+        const int32_t g = lane < cnt ? __ldg(idx + base + lane) : 0;
+        for (int k = 0; k < cnt; k += 8) {
+            float4 r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int32_t gk = __shfl_sync(0xffffffffu, g, (k + u) & 31);
+                for (int v = 0; v < VEC; ++v) {
+                    if (MODE == 0) {
+                        r[u] = (k + u < cnt) ? __ldg(reinterpret_cast<const float4 *>(table) + (size_t)gk * D4 + v * 32 + lane)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                        acc.x += r[u].x; acc.y += r[u].y; acc.z += r[u].z; acc.w += r[u].w;
+                    } else if (k + u < cnt) {
+                        float *dst = grad + ((size_t)gk * D4 + v * 32 + lane) * 4;
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(one.x), "f"(one.y),
+                                     "f"(one.z), "f"(one.w) : "memory");
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == 0 && sink) sink[(warp * 32 + lane) & 1023] = acc.x + acc.y + acc.z + acc.w;
+}
+
 }  // namespace g2v
 
 using namespace g2v;
+
+extern "C" int g2v_test_l2_rows(const float *table, float *grad, const int32_t *idx, int64_t n_idx, int32_t D,
+                                int32_t mode, float *sink, void *stream) {
+    G2V_REQUIRE(idx && n_idx >= 0 && D > 0 && D % 128 == 0 && (mode == 0 ? (table && sink) : (grad != nullptr)),
+                "g2v_test_l2_rows: bad arguments");
+    if (n_idx == 0) return 0;
+    DeviceProps dp;
+    if (device_props(&dp)) return 1;
+    const int grid = dp.sm_count * 8;
+    if (mode == 0) l2_rows_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(table, grad, idx, n_idx, D / 128, sink);
+    else l2_rows_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(table, grad, idx, n_idx, D / 128, sink);
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
 
 extern "C" int g2v_abi_version(void) { return G2V_ABI_VERSION; }
 extern "C" const char *g2v_last_error(void) { return g_err; }

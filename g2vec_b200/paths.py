@@ -51,6 +51,15 @@ def canonical_rows(nodes, lens=None):
     return rows[perm[first]]
 
 
+def unique_rows(rows, key):
+    """The set of G2Vec.py:351 from rows that are ALREADY canonical (sorted, PAD-padded) with their 64-bit keys --
+    what ``walks.generate_paths(..., canonical=True)`` returns: first occurrences in ascending key order."""
+    if rows.shape[0] == 0:
+        return rows
+    perm, first = _mark(rows, key)
+    return rows[perm[first]]
+
+
 def integrate(rows_good, rows_poor):
     """integrate_pathSet (G2Vec.py:310-322): remove paths present in both groups, label the rest
     (0 = good, 1 = poor).  Returns (rows [N, L] PAD-padded, labels uint8 [N]); good rows first."""

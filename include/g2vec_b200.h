@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define G2V_ABI_VERSION 1
+#define G2V_ABI_VERSION 2
 
 /* optimizer codes for g2v_cbow_update */
 #define G2V_OPT_ADAM_TF1 0 /* tf.train.AdamOptimizer, G2Vec.py:246 (parity default) */
@@ -260,6 +260,11 @@ int g2v_paths_mark(const int32_t *rows, const int64_t *key_sorted, const int64_t
  * kernel's own Philox, and the same words from curand's Philox4_32_10 generator
  * (curand_init(seed, subsequence, 0)), to prove the stream is curand-compatible.
  * ------------------------------------------------------------------------------------- */
+/* Measurement hook: (mode 0) read / (mode 1) red.add a constant into the rows idx[0..n_idx) of a [*, D] float
+ * table, D a multiple of 128 -- the memory operations of the CBOW kernels without the arithmetic; bench.py times it
+ * on an L2-resident table to get the L2 ceiling the fused kernel is compared with.  sink: >= 1024 floats. */
+int g2v_test_l2_rows(const float *table, float *grad, const int32_t *idx, int64_t n_idx, int32_t D, int32_t mode,
+                     float *sink, void *stream);
 int g2v_test_draws(uint64_t seed, uint64_t subsequence, int32_t n, uint64_t *out_dev, void *stream);
 int g2v_test_curand_draws(uint64_t seed, uint64_t subsequence, int32_t n, uint64_t *out_dev,
                           void *stream);

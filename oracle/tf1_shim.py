@@ -22,12 +22,14 @@ re-stated here, each from TF 1.x's published definition, in float32 on torch-CPU
                               oracle and the GPU path are given the very same initial tensors.
 * ``tf.sigmoid`` / ``>`` / ``tf.cast`` / ``tf.equal`` -> elementwise, ``(sigmoid(O) > 0.5) == Y`` as written.
 
-``trace`` records every Session.run / Tensor.eval in call order so the golden generator can store the
-per-step accuracies the reference computes but prints only every 5th step.
+``trace`` records every Session.run / Tensor.eval in call order, as (kind, scalar value or None, perf_counter
+time), so the golden generator can store the per-step accuracies the reference computes but prints only every
+5th step, and bench.py can time the training loop of the unmodified function.
 """
 import contextlib
 import math
 import sys
+import time
 import types
 
 import numpy as np
@@ -231,7 +233,7 @@ class Session:
     def run(self, fetches, feed_dict=None):
         if isinstance(fetches, _TrainOp):
             out = fetches._run(feed_dict)
-            _state["trace"].append(("train", None))
+            _state["trace"].append(("train", None, time.perf_counter()))
             return out
         if isinstance(fetches, _InitOp):
             return fetches.run()
@@ -242,7 +244,8 @@ class Session:
             out = out[()]                                     # numpy scalar, as TF returns
         else:
             out = out.copy()
-        _state["trace"].append(("var" if isinstance(fetches, Variable) else "eval", out if out.ndim == 0 else None))
+        _state["trace"].append(("var" if isinstance(fetches, Variable) else "eval", out if out.ndim == 0 else None,
+                                time.perf_counter()))
         return out
 
 

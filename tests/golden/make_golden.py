@@ -54,7 +54,7 @@ def run_reference_cbow(rowptr, gene, label, V, D, lr, seed):
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         W = ref.compute_genetovec(P, V, D, lr)
-    accs = [float(v) for k, v in tf1_shim.trace() if k == "eval"]       # val, tr, val, tr, ... (:266-267)
+    accs = [float(e[1]) for e in tf1_shim.trace() if e[0] == "eval"]       # val, tr, val, tr, ... (:266-267)
     W0, Wo0 = tf1_shim.initial_values()
     log = re.sub(r"\([0-9.]+ sec\)", "(T sec)", buf.getvalue())
     return W, np.array(accs[0::2], dtype=np.float32), np.array(accs[1::2], dtype=np.float32), W0, Wo0.reshape(-1), log

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.g2v_abi_version() == 1
+    assert lib.g2v_abi_version() == 2
 
 
 def test_no_cpu_fallback_calls_fail_loudly():

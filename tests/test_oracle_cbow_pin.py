@@ -82,7 +82,7 @@ def test_golden_is_what_the_reference_produces_now():
     with contextlib.redirect_stdout(io.StringIO()):
         W = ref.compute_genetovec(P, g["V"], g["D"], g["lr"])
     assert np.abs(W - g["W_ref"]).max() < 1e-6 * np.abs(g["W_ref"]).max()     # BLAS thread count may differ
-    accs = [float(v) for k, v in tf1_shim.trace() if k == "eval"]
+    accs = [float(e[1]) for e in tf1_shim.trace() if e[0] == "eval"]
     assert np.allclose(accs[0::2], g["acc_val"], atol=1e-7) and len(accs) // 2 - 1 == g["stop_step"]
     W0, Wo0 = tf1_shim.initial_values()
     assert (W0 == g["W0"]).all() and (Wo0.reshape(-1) == g["Wo0"]).all()
