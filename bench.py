@@ -245,8 +245,12 @@ def run_b200(args):
         D = hidden or D
         graphs = [g2v.WalkGraph(rp, col, weights=w) for rp, col, w in gs]
         n_walk = g2v.walks.num_walkers(V, reps_total, rank, None, world)
-        outs = [(torch.empty((n_walk, L), dtype=torch.int32, device=dev), torch.empty((n_walk,), dtype=torch.int32, device=dev),
-                 torch.empty((n_walk,), dtype=torch.int64, device=dev)) for _ in (0, 1)]
+        # both groups' rows in ONE buffer (group 0 first): the set pipeline then needs no concatenation
+        all_rows = torch.empty((2 * n_walk, L), dtype=torch.int32, device=dev)
+        all_lens = torch.empty((2 * n_walk,), dtype=torch.int32, device=dev)
+        all_keys = torch.empty((2 * n_walk,), dtype=torch.int64, device=dev)
+        outs = [(all_rows[g * n_walk:(g + 1) * n_walk], all_lens[g * n_walk:(g + 1) * n_walk],
+                 all_keys[g * n_walk:(g + 1) * n_walk]) for g in (0, 1)]
 
         def walk_pass(canonical=True):
             for g in (0, 1):
@@ -295,11 +299,10 @@ def run_b200(args):
             res["walk_e2e"] = {"value": visits / dt, "unit": "steps/s", "h2d_bytes_per_step": int(csr_b),
                                "d2h_bytes_per_step": int(2 * n_walk * (L + 1) * 4), "api": "g2v_walk_host (C ABI, host buffers)"}
 
-        # ---- windows from the walks (dedup of canonical rows, cross-group removal, CSR)
-        rows = [paths.unique_rows(outs[g][0], outs[g][2]) for g in (0, 1)]
-        prow, plab = paths.integrate(rows[0], rows[1])
-        rowptr, gene, label = paths.windows_csr(prow, plab)
-        del rows, prow, plab, outs
+        # ---- windows from the walks: set semantics of G2Vec.py:351,313 + CSR + geneFreq (csrc/g2v_paths.cu)
+        grp = torch.cat([torch.zeros(n_walk, dtype=torch.uint8, device=dev), torch.ones(n_walk, dtype=torch.uint8, device=dev)])
+        rowptr, gene, label, _code = paths.build_windows(all_rows, all_lens, all_keys, grp, V)   # sort-free set pipeline
+        del all_rows, all_lens, all_keys, grp, outs
         N_loc = int(rowptr.shape[0]) - 1
         lens_np = np.diff(rowptr.cpu().numpy()).astype(np.int64)
         tr, va = cbow.split_indices(N_loc, 1000 + rank)

@@ -196,33 +196,41 @@ def main(argv=None):
     idx = {g: i for i, g in enumerate(data['gene'])}
     src = np.fromiter((idx[e[0]] for e in network['edge']), dtype=np.int32, count=len(network['edge']))
     dst = np.fromiter((idx[e[1]] for e in network['edge']), dtype=np.int32, count=len(network['edge']))
-    rows = []
+    import torch
+    n_total = n_genes * args.numRepetition                     # walkers per group: w = repetition * n_genes + start gene
+    L = args.lenPath
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows = torch.empty((2 * n_total, L), dtype=torch.int32, device=dev)
+    lens = torch.empty(2 * n_total, dtype=torch.int32, device=dev)
+    key = torch.empty(2 * n_total, dtype=torch.int64, device=dev)
     for i, _group in enumerate(['g', 'p']):
         rp, col, w = graph.group_csr_gpu(data['expr'], data['label'], i, src, dst)
         wg = walks.WalkGraph(rp, col, weights=w)
-        # walkers rank, rank+world, ...: no collective during the walk (counter-based RNG), one all_gather after
-        nodes, lens = walks.generate_paths(wg, args.lenPath, args.numRepetition, seed=args.seed, group=i,
-                                           walker_begin=rank, walker_stride=world)
-        r = paths.canonical_rows(nodes, lens)
-        if dist is not None:
-            import torch
-            cnt = torch.tensor([r.shape[0]], dtype=torch.int64, device=r.device)
-            cnts = [torch.zeros_like(cnt) for _ in range(world)]
-            dist.all_gather(cnts, cnt)
-            m = int(max(int(c[0]) for c in cnts))
-            pad = torch.full((m, r.shape[1]), paths.PAD, dtype=r.dtype, device=r.device)
-            pad[:r.shape[0]] = r
-            parts = [torch.empty_like(pad) for _ in range(world)]
-            dist.all_gather(parts, pad)
-            # same content-determined row order as on one GPU (ascending key), so that --seed picks the same
-            # train/validation split whatever the number of GPUs
-            r = paths.canonical_rows(torch.cat([p[:int(c[0])] for p, c in zip(parts, cnts)], dim=0).contiguous())
-        rows.append(r)
-    prow, plab = paths.integrate(rows[0], rows[1])
-    w_rowptr, w_gene, w_label = paths.windows_csr(prow, plab)
-    code = paths.gene_freq_codes(w_rowptr, w_gene, w_label, n_genes)
+        sl = slice(i * n_total, (i + 1) * n_total)
+        if dist is None:
+            # tuple(sorted(path)) is fused into the sampler: sorted rows + their 64-bit keys come back
+            walks.generate_paths(wg, L, args.numRepetition, seed=args.seed, group=i, canonical=True,
+                                 out=(rows[sl], lens[sl], key[sl]))
+        else:
+            # walkers rank, rank+world, ...: no collective during the walk (counter-based RNG); one all_gather after,
+            # rows put back at their walker index so that every rank holds the 1-GPU arrays (same window order,
+            # hence the same --seed split, whatever the number of GPUs)
+            r_, l_, k_ = walks.generate_paths(wg, L, args.numRepetition, seed=args.seed, group=i, canonical=True,
+                                              walker_begin=rank, walker_stride=world)
+            per = -(-n_total // world)
+            pad_r = torch.full((per, L), paths.PAD, dtype=torch.int32, device=dev); pad_r[:r_.shape[0]] = r_
+            pad_l = torch.zeros(per, dtype=torch.int32, device=dev); pad_l[:l_.shape[0]] = l_
+            pad_k = torch.zeros(per, dtype=torch.int64, device=dev); pad_k[:k_.shape[0]] = k_
+            gr, gl, gk = ([torch.empty_like(t) for _ in range(world)] for t in (pad_r, pad_l, pad_k))
+            dist.all_gather(gr, pad_r); dist.all_gather(gl, pad_l); dist.all_gather(gk, pad_k)
+            for r in range(world):
+                cnt = len(range(r, n_total, world))
+                rows[sl][r::world] = gr[r][:cnt]; lens[sl][r::world] = gl[r][:cnt]; key[sl][r::world] = gk[r][:cnt]
+    group = torch.cat([torch.zeros(n_total, dtype=torch.uint8, device=dev), torch.ones(n_total, dtype=torch.uint8, device=dev)])
+    w_rowptr, w_gene, w_label, code = paths.build_windows(rows, lens, key, group, n_genes)
+    del rows, lens, key, group
     geneFreq = paths.gene_freq_dict(code, data['gene'])
-    print("    n_paths : %d" % prow.shape[0])
+    print("    n_paths : %d" % int(w_label.shape[0]))
     print("    n_genes : %d\t(genes in good or poor random paths)" % len(geneFreq))
 
     print(">>> 4. Compute distributed representations using modified CBOW")

@@ -245,6 +245,33 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
         int32_t *row = out_nodes + (size_t)t * (size_t)L;
         if (!CANON) {
             for (int i = lane; i < L; i += 32) row[i] = (i < n) ? smem[path + i] : -1;     // visit order
+        } else if (BITMAP) {
+            // tuple(sorted(path)) (G2Vec.py:345) read off the visited bitmap: the set bits in index order ARE the
+            // sorted path.  Lane l owns the words [l*B, (l+1)*B): count, one warp scan for its first output
+            // position, then emit its bits in order (and clear the words: the next walker starts from zero).
+            const int32_t lastn = smem[path + n - 1];            // the final node is appended but never inserted
+            smem[hs + (lastn >> 5)] |= (1 << (lastn & 31));
+            __syncwarp();
+            const int B = (H + 31) >> 5, w0 = lane * B, w1 = min(H, w0 + B);
+            uint32_t cnt = 0;
+            for (int wi = w0; wi < w1; ++wi) cnt += __popc((uint32_t)smem[hs + wi]);
+            uint32_t pos = warp_inclusive_scan_u32(cnt, lane) - cnt;
+            uint64_t h = 0;
+            for (int wi = w0; wi < w1; ++wi) {
+                uint32_t bits = (uint32_t)smem[hs + wi];
+                if (bits) smem[hs + wi] = 0;
+                while (bits) {
+                    const int32_t v = wi * 32 + (__ffs(bits) - 1);
+                    bits &= bits - 1;
+                    row[pos] = v;
+                    h += path_key_term(v, (int)pos);
+                    ++pos;
+                }
+            }
+            for (int i = n + lane; i < L; i += 32) row[i] = kPathPad;
+            h = warp_sum_u64(h);
+            if (lane == 0) out_key[t] = path_key_finish(h);
+            dirty = false;                                       // already cleared
         } else {
             // tuple(sorted(path)) (G2Vec.py:345): bitonic network over the next power of two, INT32_MAX padding
             int P2 = 1;

@@ -112,8 +112,48 @@ def gene_freq_codes(rowptr, gene, labels, n_genes):
 
 
 def gene_freq_dict(code, gene_names):
-    code = code.cpu().numpy()
+    code = code.cpu().numpy().astype(np.int64)
     return {gene_names[i]: int(c) for i, c in enumerate(code) if c >= 0}
+
+
+def build_windows(rows, lens, key, group, n_genes):
+    """From the sampler's canonical output of BOTH groups to the trainer's input, without a sort
+    (csrc/g2v_paths.cu, g2v_paths_set_*): ``rows`` int32 [n, L] sorted + PAD-padded, ``lens`` int32 [n], ``key``
+    int64 [n] (walks.generate_paths(..., canonical=True)), ``group`` uint8 [n] (0 good / 1 poor).
+
+    Returns (rowptr int32 [N+1], gene int32 [nnz], label uint8 [N], code int8 [n_genes]): the CSR windows of
+    integrate_pathSet (G2Vec.py:310-322) -- duplicates inside a group and paths common to both groups removed, kept
+    rows in input order, i.e. first occurrence in (group, repetition, start gene) order -- and count_geneFreq's vote
+    per gene (:288-308; -1 = gene in no path).  A 64-bit key shared by two different rows (never observed) makes the
+    function fall back to the exact sort-based path."""
+    from . import _capi
+    lib = _capi.load()
+    rows, lens, key, group = rows.contiguous(), lens.contiguous(), key.contiguous(), group.contiguous()
+    n, L = rows.shape
+    dev = rows.device
+    st = torch.cuda.current_stream(dev).cuda_stream
+    ws = torch.empty(max(int(lib.g2v_paths_set_workspace_bytes(n)), 8), dtype=torch.uint8, device=dev)
+    keep = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    totals = torch.zeros(3, dtype=torch.int64, device=dev)
+    _capi.check(lib.g2v_paths_set_select(rows.data_ptr(), key.data_ptr(), group.data_ptr(), lens.data_ptr(), n, L,
+                                         ws.data_ptr(), keep.data_ptr(), totals.data_ptr(), st), "g2v_paths_set_select")
+    kept, nnz, clashes = (int(x) for x in totals.cpu())          # the pipeline's one host sync: sizes of the outputs
+    if clashes:                                                   # exact path: sort by key + full row comparisons
+        g0, g1 = group == 0, group == 1
+        prow, plab = integrate(unique_rows(rows[g0], key[g0]), unique_rows(rows[g1], key[g1]))
+        rowptr, gene, label = windows_csr(prow, plab)
+        return rowptr, gene, label, gene_freq_codes(rowptr, gene, label, n_genes).to(torch.int8)
+    if nnz >= 2**31:
+        raise ValueError("too many window entries for int32 CSR")
+    rowptr = torch.empty(kept + 1, dtype=torch.int32, device=dev)
+    gene = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+    label = torch.empty(max(kept, 1), dtype=torch.uint8, device=dev)[:kept]
+    freq = torch.empty(2 * n_genes, dtype=torch.int32, device=dev)
+    code = torch.empty(n_genes, dtype=torch.int8, device=dev)
+    _capi.check(lib.g2v_paths_set_emit(rows.data_ptr(), group.data_ptr(), lens.data_ptr(), keep.data_ptr(), n, L,
+                                       int(n_genes), ws.data_ptr(), kept, nnz, rowptr.data_ptr(), gene.data_ptr(),
+                                       label.data_ptr(), freq.data_ptr(), code.data_ptr(), st), "g2v_paths_set_emit")
+    return rowptr, gene, label, code
 
 
 def rows_to_set(rows):

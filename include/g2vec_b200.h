@@ -256,6 +256,27 @@ int g2v_paths_mark(const int32_t *rows, const int64_t *key_sorted, const int64_t
                    int64_t n, int32_t L, uint8_t *flag, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Between the two hot paths, sort-free form: from the canonical rows of BOTH groups (sorted,
+ * INT32_MAX padded, with their 64-bit keys and lengths -- what g2v_walk_launch_packed writes with out_key) to the
+ * trainer's input: `pathSet.add` (G2Vec.py:351), `pathSet - commonPath` (:313), the rows of integrate_pathSet
+ * (:316-320) as CSR windows, and count_geneFreq (:288-308).
+ * g2v_paths_set_select: keep[i] = 1 iff row i is the first occurrence of its content in its group (group[i] in
+ *   {0,1}; NULL = one group) and no row of the other group has the same content.  totals (device, 3 x int64) =
+ *   {rows kept, their total length, key collisions}; if collisions != 0 two different contents shared a key and the
+ *   caller must use the exact sort-based functions above instead (never observed; ~n^2/2^64).
+ * g2v_paths_set_emit: the kept rows in input order as CSR windows (rowptr [kept+1], gene [nnz], label [kept] = the
+ *   row's group) and, if freq/code are given, code[g] = 0 / 1 / 2 / -1: more good paths / more poor / tie / gene in
+ *   no kept path (freq: 2*V int32 scratch).  Synchronises the stream.
+ * workspace: g2v_paths_set_workspace_bytes(n) bytes, the same buffer for both calls.
+ * ------------------------------------------------------------------------------------- */
+size_t g2v_paths_set_workspace_bytes(int64_t n);
+int g2v_paths_set_select(const int32_t *rows, const int64_t *key, const uint8_t *group, const int32_t *len, int64_t n,
+                         int32_t L, void *workspace, uint8_t *keep, int64_t *totals, void *stream);
+int g2v_paths_set_emit(const int32_t *rows, const uint8_t *group, const int32_t *len, const uint8_t *keep, int64_t n,
+                       int32_t L, int32_t V, const void *workspace, int64_t kept, int64_t nnz, int32_t *rowptr,
+                       int32_t *gene, uint8_t *label, int32_t *freq, int8_t *code, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * Test hooks (used by tests/ only): 64-bit draws 0..n-1 of one walker subsequence from the
  * kernel's own Philox, and the same words from curand's Philox4_32_10 generator
  * (curand_init(seed, subsequence, 0)), to prove the stream is curand-compatible.

@@ -86,3 +86,74 @@ def test_canonicalise_sorts_rows_of_any_length():
         assert (rows == want).all() and (key >= 0).all() and key[7] == key[3]
         uniq = paths.canonical_rows(torch.from_numpy(nodes).cuda())
         assert paths.rows_to_set(uniq) == {tuple(int(x) for x in r[r != paths.PAD]) for r in want}
+
+
+def _walk_both_groups(g2v, reps, L, seed):
+    """Canonical rows of both ex_* groups in one buffer: (rows, lens, key, group) device tensors."""
+    import torch
+    V = 7523
+    n = reps * V
+    rows = torch.empty((2 * n, L), dtype=torch.int32, device="cuda")
+    lens = torch.empty(2 * n, dtype=torch.int32, device="cuda")
+    key = torch.empty(2 * n, dtype=torch.int64, device="cuda")
+    for g in (0, 1):
+        rp, col, w = helpers.ex_graph(g)
+        wg = g2v.WalkGraph(rp, col, weights=w)
+        g2v.generate_paths(wg, L, reps, seed=seed, group=g, canonical=True,
+                           out=(rows[g * n:(g + 1) * n], lens[g * n:(g + 1) * n], key[g * n:(g + 1) * n]))
+    group = torch.cat([torch.zeros(n, dtype=torch.uint8, device="cuda"), torch.ones(n, dtype=torch.uint8, device="cuda")])
+    return rows, lens, key, group
+
+
+def test_sort_free_pipeline_equals_oracle_on_ex():
+    """g2v_paths_set_select / _emit (hash table on the row keys, prefix sums, one emit kernel): the windows are the
+    oracle's set of (label, path), in first-occurrence order, and the gene-frequency codes are count_geneFreq's."""
+    import numpy as np
+    import g2vec_b200 as g2v
+    from g2vec_b200 import paths
+    reps, L, seed = 2, 80, 0
+    (o_rowptr, o_gene, o_label), o_rows = helpers.ex_windows(reps=reps, L=L, seed=seed)
+    rows, lens, key, group = _walk_both_groups(g2v, reps, L, seed)
+    rowptr, gene, label, code = paths.build_windows(rows, lens, key, group, 7523)
+    rp, ge, la = rowptr.cpu().numpy(), gene.cpu().numpy(), label.cpu().numpy()
+    got = [(int(la[i]), tuple(int(x) for x in ge[rp[i]:rp[i + 1]])) for i in range(len(la))]
+    assert len(got) == len(set(got)) == len(o_rows) and set(got) == set(o_rows)
+    assert rp[0] == 0 and rp[-1] == len(o_gene) == len(ge)
+    # input order = first occurrence in (group, repetition, start gene) order: group 0 windows first, and within a
+    # group the walker index of the first walk that produced each path is increasing
+    assert (np.diff(la.astype(np.int8)) >= 0).all()
+    r_h, l_h, g_h = rows.cpu().numpy(), lens.cpu().numpy(), group.cpu().numpy()
+    first = {}
+    for i in range(len(l_h)):
+        first.setdefault((int(g_h[i]), tuple(int(x) for x in r_h[i, :l_h[i]])), i)
+    order = [first[w] for w in got]
+    assert order == sorted(order)
+    want = legacy.count_geneFreq(o_rows)
+    c = code.cpu().numpy()
+    assert {i: int(x) for i, x in enumerate(c) if x >= 0} == want
+
+
+def test_sort_free_pipeline_small_cases_and_collision_fallback(monkeypatch):
+    """Hand-made rows: duplicates inside a group, a path common to both groups (removed from both), empty input; and
+    keys that collide on purpose -- different rows, same key -- which must be detected and routed to the exact path."""
+    import numpy as np
+    import torch
+    from g2vec_b200 import paths
+    P = paths.PAD
+    rows = np.array([[1, 2, 3, P], [1, 2, 3, P], [4, P, P, P], [2, 5, P, P],      # group 0: a duplicate
+                     [4, P, P, P], [2, 5, 6, P], [7, 8, 9, 10], [7, 8, 9, 10]], dtype=np.int32)   # group 1: (4,) is common
+    lens = np.array([3, 3, 1, 2, 1, 3, 4, 4], dtype=np.int32)
+    group = np.array([0, 0, 0, 0, 1, 1, 1, 1], dtype=np.uint8)
+    want = [(0, (1, 2, 3)), (0, (2, 5)), (1, (2, 5, 6)), (1, (7, 8, 9, 10))]
+    r_d, l_d, g_d = (torch.from_numpy(a).cuda() for a in (rows, lens, group))
+    _, key = paths._canon(r_d)
+    for k_d in (key, torch.full_like(key, 12345)):                  # real keys; then everything on ONE key
+        rowptr, gene, label, code = paths.build_windows(r_d, l_d, k_d, g_d, 12)
+        rp, ge, la = rowptr.cpu().numpy(), gene.cpu().numpy(), label.cpu().numpy()
+        got = [(int(la[i]), tuple(int(x) for x in ge[rp[i]:rp[i + 1]])) for i in range(len(la))]
+        assert sorted(got) == sorted(want)
+        c = code.cpu().numpy()
+        assert list(c) == [-1, 0, 0, 0, -1, 2, 1, 1, 1, 1, 1, -1]     # gene 5: one good + one poor path = tie; 4: only in the common path
+    e = torch.empty((0, 4), dtype=torch.int32, device="cuda")
+    rowptr, gene, label, code = paths.build_windows(e, l_d[:0], key[:0], g_d[:0], 12)
+    assert rowptr.cpu().tolist() == [0] and gene.numel() == 0 and label.numel() == 0 and (code.cpu().numpy() == -1).all()
