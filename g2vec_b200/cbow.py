@@ -62,7 +62,7 @@ class CbowModel:
     """Parameters + optimizer state + scratch in HBM, and the three kernel calls."""
 
     def __init__(self, rowptr, gene, label, n_genes, hidden, W_ih0, W_ho0, optimizer="adam", reduce="sum",
-                 lr=0.005, beta1=0.9, beta2=0.999, eps=1e-8, device=None, algo="rows"):
+                 lr=0.005, beta1=0.9, beta2=0.999, eps=1e-8, device=None, algo="rows", nvl_group=None):
         if not torch.cuda.is_available():
             raise RuntimeError("g2vec_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _capi.load()
@@ -78,8 +78,22 @@ class CbowModel:
         self.gene = to(gene, torch.int32)
         self.label = to(label, torch.uint8)
         self.V, self.D = int(n_genes), int(hidden)
-        self.W_ih = to(W_ih0, torch.float32).reshape(self.V, self.D).clone()
-        self.W_ho = to(W_ho0, torch.float32).reshape(self.D).clone()
+        n_flat = self.V * self.D + self.D
+        # rows: parameters, Adam state and gradient are flat [W_ih (V*D) | W_ho (D)] allocations.  With a process
+        # group (multi-GPU) the parameters and the gradient live in symmetric memory (peer-mapped, NVLS multicast if
+        # the fabric has it) and the optimizer step does the gradient exchange itself (g2v_cbow_update_nvl).
+        self.nvl = None
+        if algo == "rows" and nvl_group is not None:
+            self.nvl = _nvl_setup(nvl_group, n_flat, dev)
+        if algo == "rows":
+            self.w_flat = self.nvl["w"] if self.nvl else torch.empty(n_flat, dtype=torch.float32, device=dev)
+            self.W_ih = self.w_flat[:self.V * self.D].view(self.V, self.D)
+            self.W_ho = self.w_flat[self.V * self.D:]
+            self.W_ih.copy_(to(W_ih0, torch.float32).reshape(self.V, self.D))
+            self.W_ho.copy_(to(W_ho0, torch.float32).reshape(self.D))
+        else:
+            self.W_ih = to(W_ih0, torch.float32).reshape(self.V, self.D).clone()
+            self.W_ho = to(W_ho0, torch.float32).reshape(self.D).clone()
         self.opt = {"adam": _capi.OPT_ADAM_TF1, "sgd": _capi.OPT_SGD}[optimizer]
         self.reduce = {"sum": _capi.REDUCE_SUM, "mean": _capi.REDUCE_MEAN}[reduce]
         self.lr, self.beta1, self.beta2, self.eps = float(lr), float(beta1), float(beta2), float(eps)
@@ -89,7 +103,7 @@ class CbowModel:
         self.algo = algo
         if algo == "rows":
             # one allocation [g_ih | g_ho]: a multi-GPU step all-reduces the whole gradient with ONE collective
-            self.g_flat = z(self.V * self.D + self.D)
+            self.g_flat = self.nvl["g"].zero_() if self.nvl else z(n_flat)
             self.g_ih = self.g_flat[:self.V * self.D].view(self.V, self.D)
             self.g_ho = self.g_flat[self.V * self.D:]
             self.s = self.c = None
@@ -97,7 +111,13 @@ class CbowModel:
             self.g_ih = None
             self.g_ho = z(int(self.lib.g2v_cbow_r1_scratch_bytes(self.D)) // 4)   # per-block partials of W_ih^T.c
             self.s, self.c = z(self.V), z(self.V)
-        if self.opt == _capi.OPT_ADAM_TF1:
+        self.m_flat = self.v_flat = None
+        if self.opt == _capi.OPT_ADAM_TF1 and algo == "rows":
+            self.m_flat, self.v_flat = z(n_flat), z(n_flat)
+            vd = self.V * self.D
+            self.m_ih, self.v_ih = self.m_flat[:vd].view(self.V, self.D), self.v_flat[:vd].view(self.V, self.D)
+            self.m_ho, self.v_ho = self.m_flat[vd:], self.v_flat[vd:]
+        elif self.opt == _capi.OPT_ADAM_TF1:
             self.m_ih, self.v_ih, self.m_ho, self.v_ho = z(self.V, self.D), z(self.V, self.D), z(self.D), z(self.D)
         else:
             self.m_ih = self.v_ih = self.m_ho = self.v_ho = None
@@ -158,8 +178,16 @@ class CbowModel:
         return slabs.get((self._ptr(win), int(win_begin), int(n))) if slabs else None
 
     def grad_tensors(self):
-        """What a multi-GPU step must all-reduce (sum) between fwdbwd() and update()."""
+        """What a multi-GPU step must all-reduce (sum) between fwdbwd() and update(): nothing when update() does
+        the exchange itself over NVLink (self.nvl)."""
+        if self.nvl:
+            return []
         return [self.g_flat] if self.algo == "rows" else [self.c]
+
+    def exchange(self):
+        if self.nvl:
+            return "nvl-multicast (multimem.ld_reduce / multimem.st)" if self.nvl["g_mc"] else "nvl-p2p (peer loads / stores)"
+        return "nccl all_reduce"
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -220,6 +248,18 @@ class CbowModel:
                                              adev, self._stream())
             _capi.check(rc, "g2v_cbow_r1_update")
             return
+        if self.nvl:
+            # gradient exchange fused with the optimizer: barrier (every rank's gradient complete) -> reduce-scatter +
+            # Adam on the owned slice + all-gather of the new weights in ONE kernel -> barrier (weights delivered)
+            nv = self.nvl
+            nv["hg"].barrier(channel=0)
+            rc = self.lib.g2v_cbow_update_nvl(nv["hg"].buffer_ptrs_dev, nv["hw"].buffer_ptrs_dev, nv["g_mc"], nv["w_mc"],
+                                              self._ptr(self.m_flat), self._ptr(self.v_flat),
+                                              self.V * self.D + self.D, nv["rank"], nv["world"], self.opt, self.lr,
+                                              self.beta1, self.beta2, self.eps, self.t, adev, self._stream())
+            _capi.check(rc, "g2v_cbow_update_nvl")
+            nv["hg"].barrier(channel=1)
+            return
         rc = self.lib.g2v_cbow_update(self.W_ih.data_ptr(), self.W_ho.data_ptr(), self._ptr(self.m_ih),
                                       self._ptr(self.v_ih), self._ptr(self.m_ho), self._ptr(self.v_ho),
                                       self.g_ih.data_ptr(), self.g_ho.data_ptr(), self.V, self.D, self.opt,
@@ -251,6 +291,32 @@ class CbowModel:
 
     def loss_sum(self, acc_host):
         return float(acc_host[:1].view(torch.float64)[0])
+
+
+def _nvl_setup(group, n_flat, dev):
+    """Symmetric-memory buffers for the parameters and the gradient (torch.distributed._symmetric_memory: peer-mapped
+    allocations + signal pads for cross-GPU barriers; NVLS multicast address when the NVSwitch fabric offers it).
+    Returns None -- the caller then uses NCCL -- if G2V_CBOW_NVL=0 or the rendezvous is not possible on this box."""
+    import os
+    import sys
+    if os.environ.get("G2V_CBOW_NVL", "1") == "0":
+        return None
+    try:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        w = symm.empty(n_flat, dtype=torch.float32, device=dev)
+        g = symm.empty(n_flat, dtype=torch.float32, device=dev)
+        hw, hg = symm.rendezvous(w, group), symm.rendezvous(g, group)
+        mc = os.environ.get("G2V_CBOW_NVL_MULTICAST", "1") != "0"
+        w_mc = int(hw.multicast_ptr or 0) if mc else 0       # 0: no NVLS multicast object behind this allocation
+        g_mc = int(hg.multicast_ptr or 0) if mc else 0
+        if not (w_mc and g_mc):
+            w_mc = g_mc = 0
+        return {"w": w, "g": g, "hw": hw, "hg": hg, "w_mc": w_mc, "g_mc": g_mc, "rank": dist.get_rank(group),
+                "world": dist.get_world_size(group)}
+    except Exception as exc:                   # no symmetric memory here: NCCL all-reduce + replicated update instead
+        print("g2vec_b200: symmetric memory unavailable (%r); using NCCL for the gradient exchange" % (exc,), file=sys.stderr)
+        return None
 
 
 class WindowFeeder:
@@ -336,7 +402,8 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
     tr, va = split_indices(N, seed) if split is None else split
     if W_ih0 is None or W_ho0 is None:
         W_ih0, W_ho0 = init_weights(n_genes, hidden, seed)
-    model = CbowModel(win_rowptr, win_gene, labels, n_genes, hidden, W_ih0, W_ho0, optimizer, reduce, lr, algo=algo)
+    model = CbowModel(win_rowptr, win_gene, labels, n_genes, hidden, W_ih0, W_ho0, optimizer, reduce, lr, algo=algo,
+                      nvl_group=dist.group.WORLD if (dist and algo == "rows") else None)
     lens = np.diff(rowptr_np).astype(np.int64)
     n_tr, n_va = len(tr), len(va)
     full_batch = batch <= 0 or batch >= n_tr
@@ -364,7 +431,7 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
     out = out.cpu().numpy()
     if return_info:
         return out, {"history": hist, "stop_step": stop, "n_train": n_tr, "n_val": n_va, "model": model,
-                     "graph": bool(getattr(model, "loop_used_graph", False))}
+                     "graph": bool(getattr(model, "loop_used_graph", False)), "exchange": model.exchange() if dist else None}
     return out
 
 

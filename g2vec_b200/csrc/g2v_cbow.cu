@@ -351,6 +351,97 @@ cbow_update_kernel(float *__restrict__ W, float *__restrict__ M, float *__restri
     }
 }
 
+// ---- optimizer epilogue fused with the gradient exchange over NVLink / NVSwitch ---------------------------
+// Multi-GPU form of cbow_update_kernel: instead of ncclAllReduce(gradient) followed by the same dense update on
+// every rank, rank r owns the slice [r*chunk, (r+1)*chunk) of the flat parameter vector [W_ih | W_ho]:
+//   reduce-scatter   g = sum over ranks of their gradient slice -- ONE multimem.ld_reduce per 16 bytes when the
+//                    buffers are bound to an NVLS multicast object (the NVSwitch adds), else peer loads (P2P)
+//   zero             the slice of every rank's gradient buffer (multimem.st / peer stores): ready for the next step
+//   Adam / SGD       on the owned slice only -- m and v are touched for 1/world of the parameters per rank
+//   all-gather       the updated weights are stored into every rank's parameter buffer (multimem.st / peer stores)
+// so the transfer overlaps the arithmetic 16 bytes at a time and the dense update work is divided by `world`.
+// The caller brackets the launch with two cross-GPU barriers (all gradients complete before; all weights
+// delivered after).  Buffers are symmetric-memory allocations (same offset on every rank).
+__device__ __forceinline__ float4 mm_ld_reduce4(const float *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mm_st4(float *mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_peer4(const float *p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_peer4(float *p, float4 v) {
+    asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+template <int OPT, bool MC>
+__global__ void __launch_bounds__(256)
+cbow_update_nvl_kernel(float *const *__restrict__ g_ptrs, float *const *__restrict__ w_ptrs, float *__restrict__ g_mc,
+                       float *__restrict__ w_mc, float *__restrict__ M, float *__restrict__ Vv, int64_t n, int32_t rank,
+                       int32_t world, float alpha_host, float omb1, float omb2, float eps,
+                       const float *__restrict__ alpha_dev, const int32_t *__restrict__ skip) {
+    G2V_SKIP_IF_STOPPED(skip);
+    const float alpha = alpha_dev ? __ldg(alpha_dev + 2) : alpha_host;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n4 = n >> 2, chunk = (n4 + world - 1) / world;
+    const int64_t lo = (int64_t)rank * chunk, hi = min(n4, lo + chunk);
+    float *Wl = w_ptrs[rank];
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = lo + tid; i < hi; i += nth) {
+        float4 g;
+        if (MC) {
+            g = mm_ld_reduce4(g_mc + 4 * i);
+            mm_st4(g_mc + 4 * i, zero);
+        } else {
+            g = zero;
+            for (int p = 0; p < world; ++p) {
+                float *gp = g_ptrs[(rank + p) % world] + 4 * i;
+                const float4 x = ld_peer4(gp);
+                g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+                st_peer4(gp, zero);
+            }
+        }
+        float4 w = reinterpret_cast<const float4 *>(Wl)[i];
+        if (OPT == G2V_OPT_ADAM_TF1) {
+            float4 m = reinterpret_cast<float4 *>(M)[i], v = reinterpret_cast<float4 *>(Vv)[i];
+            adam1(w.x, m.x, v.x, g.x, alpha, omb1, omb2, eps);
+            adam1(w.y, m.y, v.y, g.y, alpha, omb1, omb2, eps);
+            adam1(w.z, m.z, v.z, g.z, alpha, omb1, omb2, eps);
+            adam1(w.w, m.w, v.w, g.w, alpha, omb1, omb2, eps);
+            reinterpret_cast<float4 *>(M)[i] = m; reinterpret_cast<float4 *>(Vv)[i] = v;
+        } else {
+            w.x -= alpha * g.x; w.y -= alpha * g.y; w.z -= alpha * g.z; w.w -= alpha * g.w;
+        }
+        if (MC) {
+            mm_st4(w_mc + 4 * i, w);
+        } else {
+            for (int p = 0; p < world; ++p) st_peer4(w_ptrs[(rank + p) % world] + 4 * i, w);
+        }
+    }
+    // scalar tail (n not a multiple of 4): the last rank, peer loads/stores
+    if (rank == world - 1)
+        for (int64_t i = (n4 << 2) + tid; i < n; i += nth) {
+            float g = 0.f;
+            for (int p = 0; p < world; ++p) {
+                volatile float *gp = g_ptrs[p] + i;
+                g += *gp; *gp = 0.f;
+            }
+            float w = Wl[i];
+            if (OPT == G2V_OPT_ADAM_TF1) adam1(w, M[i], Vv[i], g, alpha, omb1, omb2, eps);
+            else w -= alpha * g;
+            for (int p = 0; p < world; ++p) { volatile float *wp = w_ptrs[p] + i; *wp = w; }
+        }
+}
+
 int rows_grid(const void *kernel, size_t smem, int64_t n_win, int *grid_out) {
     DeviceProps dp;
     if (device_props(&dp)) return 1;
@@ -557,6 +648,45 @@ extern "C" int g2v_cbow_update(float *W_ih, float *W_ho, float *m_ih, float *v_i
         cbow_update_kernel<G2V_OPT_SGD><<<(unsigned)blocks, 256, 0, st>>>(
             W_ih, nullptr, nullptr, g_ih, n, W_ho, nullptr, nullptr, g_ho, (int64_t)D, lr, 0.f, 0.f, 0.f, nullptr, loop_skip_flag());
     }
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+extern "C" int g2v_cbow_update_nvl(float *const *g_ptrs_dev, float *const *w_ptrs_dev, float *g_multicast,
+                                   float *w_multicast, float *m_flat, float *v_flat, int64_t n, int32_t rank,
+                                   int32_t world, int32_t optimizer, float lr, float beta1, float beta2, float eps,
+                                   int32_t t, const float *alpha_dev, void *stream) {
+    G2V_REQUIRE(n > 0 && world >= 1 && rank >= 0 && rank < world && (t >= 1 || alpha_dev), "g2v_cbow_update_nvl: bad sizes");
+    G2V_REQUIRE(g_ptrs_dev && w_ptrs_dev, "g2v_cbow_update_nvl: null pointer tables");
+    G2V_REQUIRE((g_multicast == nullptr) == (w_multicast == nullptr), "g2v_cbow_update_nvl: both or neither multicast pointer");
+    G2V_REQUIRE(optimizer == G2V_OPT_ADAM_TF1 || optimizer == G2V_OPT_SGD, "g2v_cbow_update_nvl: unknown optimizer %d", optimizer);
+    G2V_REQUIRE(optimizer == G2V_OPT_SGD || (m_flat && v_flat), "g2v_cbow_update_nvl: Adam needs m/v buffers");
+    DeviceProps dp;
+    if (device_props(&dp)) return 1;
+    const int64_t own = ((n >> 2) + world - 1) / world;
+    int64_t blocks = (own + 255) / 256;
+    const int64_t cap = (int64_t)dp.sm_count * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool mc = g_multicast != nullptr;
+    float alpha = lr, omb1 = 0.f, omb2 = 0.f;
+    if (optimizer == G2V_OPT_ADAM_TF1) {
+        float b1p = 1.f, b2p = 1.f;
+        for (int i = 0; i < t; ++i) { b1p *= beta1; b2p *= beta2; }
+        alpha = alpha_dev ? 0.f : lr * sqrtf(1.f - b2p) / (1.f - b1p);
+        omb1 = 1.f - beta1; omb2 = 1.f - beta2;
+    } else {
+        alpha_dev = nullptr;
+    }
+#define G2V_NVL(OPT, MC)                                                                                              \
+    cbow_update_nvl_kernel<OPT, MC><<<(unsigned)blocks, 256, 0, st>>>(g_ptrs_dev, w_ptrs_dev, g_multicast, w_multicast, \
+                                                                      m_flat, v_flat, n, rank, world, alpha, omb1, omb2, \
+                                                                      eps, alpha_dev, loop_skip_flag())
+    if (optimizer == G2V_OPT_ADAM_TF1) { if (mc) G2V_NVL(G2V_OPT_ADAM_TF1, true); else G2V_NVL(G2V_OPT_ADAM_TF1, false); }
+    else { if (mc) G2V_NVL(G2V_OPT_SGD, true); else G2V_NVL(G2V_OPT_SGD, false); }
+#undef G2V_NVL
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

@@ -125,6 +125,18 @@ int g2v_cbow_update(float *W_ih, float *W_ho, float *m_ih, float *v_ih, float *m
                     float *g_ih, float *g_ho, int32_t V, int32_t D, int32_t optimizer, float lr,
                     float beta1, float beta2, float eps, int32_t t, const float *alpha_dev, void *stream);
 
+/* Multi-GPU optimizer epilogue fused with the gradient exchange (one process per GPU, one node): replaces
+ * ncclAllReduce(gradient) + g2v_cbow_update.  All buffers are flat [W_ih (V*D) | W_ho (D)] = n floats, the gradient
+ * and the parameters in symmetric memory (same size on every rank, peer-mapped): g_ptrs_dev / w_ptrs_dev are DEVICE
+ * arrays of `world` pointers (entry r = rank r's buffer as seen from this rank); g_multicast / w_multicast are the
+ * NVLS multicast addresses of the same buffers, or both NULL (then peer loads/stores are used).  Rank r reduces the
+ * slice r of every rank's gradient (multimem.ld_reduce or peer loads), zeroes it everywhere, applies TF1 Adam / SGD
+ * to slice r of its m / v / parameters, and stores the new parameters into every rank's buffer.  The caller must
+ * place a cross-GPU barrier before the call (all gradients complete) and after it (all parameters delivered). */
+int g2v_cbow_update_nvl(float *const *g_ptrs_dev, float *const *w_ptrs_dev, float *g_multicast, float *w_multicast,
+                        float *m_flat, float *v_flat, int64_t n, int32_t rank, int32_t world, int32_t optimizer,
+                        float lr, float beta1, float beta2, float eps, int32_t t, const float *alpha_dev, void *stream);
+
 /* Device-resident Adam step state -- TF1 keeps beta1^t / beta2^t as variables (AdamOptimizer's
  * beta1_power / beta2_power, G2Vec.py:246).  state = {beta1^t, beta2^t, alpha_t, unused}, initialised to
  * {1, 1, 0, 0}; g2v_cbow_adam_tick advances it by one step on the device.  Passing the same pointer as

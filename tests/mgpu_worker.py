@@ -26,15 +26,25 @@ def main(out):
     (rowptr, gene, label), _ = helpers.ex_windows(reps=2)
     W0, Wo0 = helpers.init_weights(7523, 128, 0)
     # 11 steps: step 0 eagerly, then two 5-step chunks -- on N GPUs each chunk is ONE CUDA graph that contains the
-    # NCCL all-reduces (g2vec_b200.cbow._device_loop)
-    got, info = g2v.train_cbow(rowptr, gene, label, 7523, 128, 0.005, max_epoch=11, seed=0, W_ih0=W0, W_ho0=Wo0,
-                               early_stop=False, log=None, return_info=True)
+    # gradient exchange (g2vec_b200.cbow.DeviceLoop).  Three exchanges: the fused reduce-scatter + Adam + all-gather
+    # kernel over NVLink with NVLS multicast (default), the same with plain peer loads/stores, and NCCL all_reduce.
+    runs = {}
+    for name, env in (("nvl", {}), ("nvl_p2p", {"G2V_CBOW_NVL_MULTICAST": "0"}), ("nccl", {"G2V_CBOW_NVL": "0"})):
+        os.environ.update(env)
+        got, info = g2v.train_cbow(rowptr, gene, label, 7523, 128, 0.005, max_epoch=11, seed=0, W_ih0=W0, W_ho0=Wo0,
+                                   early_stop=False, log=None, return_info=True)
+        for k in env:
+            os.environ.pop(k)
+        runs[name] = (got, info)
+    got, info = runs["nvl"]
     if rank == 0:
         full = np.empty((2 * 7523, 80), np.int32); fl = np.empty(2 * 7523, np.int32)
         for r in range(world):
             full[r::world], fl[r::world] = gathered[r]
         np.savez(out, W=got, hist=np.array(info["history"], dtype=np.float64), nodes=full, lens=fl,
-                 graph=np.array(info["graph"]))
+                 graph=np.array(info["graph"]), exchange=np.array([runs[k][1]["exchange"] for k in ("nvl", "nvl_p2p", "nccl")]),
+                 W_p2p=runs["nvl_p2p"][0], W_nccl=runs["nccl"][0],
+                 hist_nccl=np.array(runs["nccl"][1]["history"], dtype=np.float64))
     dist.destroy_process_group()
 
 

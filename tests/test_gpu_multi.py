@@ -36,7 +36,12 @@ def test_two_gpus_equal_one_gpu(tmp_path):
     W0, Wo0 = helpers.init_weights(7523, 128, 0)
     ref, hist, _, _ = oracle.cbow_train(rowptr, gene, label, tr, va, W0, Wo0, 0.005, max_steps=11, early_stop=False)
     assert np.abs(z["W"] - ref).max() < 1e-4 * np.abs(ref).max()
-    print("multi-GPU chunks ran as CUDA graphs with NCCL inside:", bool(z["graph"]))
+    print("multi-GPU chunks ran as CUDA graphs with the exchange inside:", bool(z["graph"]), "| exchanges:", list(z["exchange"]))
+    assert str(z["exchange"][2]).startswith("nccl")
+    for k in ("W_p2p", "W_nccl"):                                  # every gradient-exchange path gives the same vectors
+        assert np.abs(z[k] - ref).max() < 1e-4 * np.abs(ref).max(), k
+    assert np.abs(z["W"] - z["W_nccl"]).max() < 2e-5 * np.abs(ref).max()
+    assert np.abs(z["hist"] - z["hist_nccl"]).max() <= 2.0 / len(va) + 1e-7
     assert len(z["hist"]) == 11
     for (s_, av, at), row in zip(hist, z["hist"]):
         assert abs(av - row[1]) <= 2.0 / len(va) + 1e-7 and abs(at - row[2]) <= 2.0 / len(tr) + 1e-7
