@@ -313,7 +313,8 @@ def run_b200(args):
                    windows=(rowptr, gene, label), tr_d=tr_d, va_d=va_d)
 
         def measure(algo):
-            model = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, optimizer=args.optimizer, lr=0.005, algo=algo)
+            model = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, optimizer=args.optimizer, lr=0.005, algo=algo,
+                                  nvl_group=dist.group.WORLD if (world > 1 and algo == "rows") else None)
             model.prepare_csc(tr_d)                    # rank1: transposed incidence of the static training list
             slabs = model.prepare_slabs(tr_d)          # rows, table > L2: gene-slab passes
             model.prepare_slabs(va_d)
@@ -329,7 +330,8 @@ def run_b200(args):
                      "fb_ms": float(np.mean([m[0] for m in marks])),
                      "upd_ms": allmax(float(np.mean([m[1] for m in marks]))),
                      "val_ms": allmax(float(np.mean([m[2] for m in marks]))), "slabs": bool(slabs),
-                     "n_slabs": getattr(model, "_n_slabs", 1), "model": model, "loop": loop}
+                     "n_slabs": getattr(model, "_n_slabs", 1), "model": model, "loop": loop,
+                     "exchange": model.exchange() if world > 1 else None}
                 r["step_ms"], r["graph"] = r["eager_ms"], False
                 loop.reset()
                 try:                                    # what train_cbow runs: the same launches as CUDA graphs
@@ -515,7 +517,7 @@ def run_b200(args):
             r = S["measure"]("rows")
             r.pop("model"); r.pop("loop")
             strong[wl] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["step_ms"], "windows_train": S["n_tr"],
-                          "graph": r["graph"], "gene_slabs": r["n_slabs"],
+                          "graph": r["graph"], "gene_slabs": r["n_slabs"], "exchange": r["exchange"],
                           "walk": {"value": S["visits"] / (S["walk_ms"] * 1e-3), "unit": "steps/s", "ms_per_pass": S["walk_ms"]},
                           "config": "%s: %s, hidden %d, lenPath %d, numRepetition 10 in total over %d GPU(s)"
                                     % (wl, S["desc"], S["D"], S["L"], world)}
@@ -548,8 +550,8 @@ def run_b200(args):
                        "launch": ("one CUDA graph replay per step%s (eager launches: %.3f ms per step)"
                                   % (", NCCL all-reduces inside the graph" if world > 1 else "", main["eager_ms"]))
                                  if main.get("graph") else "eager launches",
-                       "parallelism": "dp%d (windows/walkers sharded, W replicated, ONE dense all-reduce of [g_ih|g_ho] "
-                                      "+ one of the 3 counters per step)" % world,
+                       "parallelism": "dp%d (windows/walkers sharded, W replicated; gradient exchange per step: %s; the 3 "
+                                      "accuracy counters: one 24-byte all_reduce)" % (world, main.get("exchange") or "none"),
                        "l2": "256 MiB flush write before every timed step"},
             "train_only": {"value": n_tr_tot / (upd_ms * 1e-3), "unit": UNIT, "ms_per_step": upd_ms,
                            "note": "fwd+bwd+all-reduce+update, without the two accuracy passes (eager launches)"},
@@ -680,6 +682,18 @@ def parity_block(g2v, dist, rank, world, dev, gs, V, L):
         err = float((m.g_flat - ref.g_flat).abs().max() / ref.g_flat.abs().max())
         out.update(grad_batch_windows=nb, grad_rel_err=err, grad_collective="one all_reduce over [g_ih | g_ho] (%d floats)"
                    % m.g_flat.numel())
+    # (c) the fused exchange + optimizer kernel (g2v_cbow_update_nvl): one Adam step of the same batch sharded over
+    #     the ranks vs the same step on rank 0 alone
+    mn = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, nvl_group=dist.group.WORLD)
+    if mn.nvl:                                                     # (NCCL-only runs have nothing to check here)
+        mn.fwdbwd(mine, nb)
+        mn.update()
+        torch.cuda.synchronize()
+        if rank == 0:
+            ref.update()
+            torch.cuda.synchronize()
+            out.update(nvl_exchange=mn.exchange(),
+                       nvl_update_rel_err=float((mn.w_flat - ref.w_flat).abs().max() / ref.w_flat.abs().max()))
     torch.cuda.synchronize()
     return out if rank == 0 else None
 

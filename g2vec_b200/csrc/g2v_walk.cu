@@ -39,8 +39,14 @@ namespace g2v {
 
 constexpr int kWalkWarps = 8;   // warps per CTA
 constexpr int kKC = 2;          // neighbour chunks kept in registers on the long-row path
-#ifndef G2V_WALK_MINB
-#define G2V_WALK_MINB 6         // resident CTAs per SM the kernels are compiled for (register cap 40)
+// resident CTAs per SM the kernels are compiled for: 6 (register cap 40) for the bitmap variants, 8 (cap 32) for the
+// hash-set variants -- measured (profiles/r2/tune_walk_minb_r2l.txt): syn10k 1.97 ms at 6 vs 2.00 ms at 8, stress200k
+// (hash set, V = 200k) 25.0 ms at 6 vs 22.0 ms at 8
+#ifndef G2V_WALK_MINB_BITMAP
+#define G2V_WALK_MINB_BITMAP 6
+#endif
+#ifndef G2V_WALK_MINB_HASH
+#define G2V_WALK_MINB_HASH 8
 #endif
 
 enum { LAY_CSR = 0, LAY_E8 = 1, LAY_E4 = 2 };
@@ -116,7 +122,7 @@ __device__ __forceinline__ int32_t pick_in_chunk(uint32_t p, uint32_t q0, int32_
 }
 
 template <bool BITMAP, int LAYOUT, bool CANON>
-__global__ void __launch_bounds__(kWalkWarps * 32, G2V_WALK_MINB)
+__global__ void __launch_bounds__(kWalkWarps * 32, BITMAP ? G2V_WALK_MINB_BITMAP : G2V_WALK_MINB_HASH)
 walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H, int32_t hshift, uint64_t seed,
             uint32_t group, int64_t walker_begin, int64_t n_walkers, int64_t walker_stride,
             int32_t *__restrict__ out_nodes, int32_t *__restrict__ out_len, unsigned long long *__restrict__ out_key,

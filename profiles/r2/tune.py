@@ -111,9 +111,34 @@ def walk(args):
                                   "pass_ms": ms, "pass_ms_min": mn, "visits": visits, "steps_per_s": visits / ms * 1e3}), flush=True)
 
 
+def fused(args):
+    """The fused fwd+bwd kernel on an L2-resident table (V=10k, D=128: BASELINE configs[1]'s shape) with the default
+    LDG.128 / RED.128 memory path and with the two TMA forms (G2V_CBOW_SCATTER=tma -> UBLKRED, G2V_CBOW_GATHER=tma ->
+    UBLKCP); under `ncu -k regex:cbow_rows_kernel` every variant contributes 5 launches in this order."""
+    V, D, L = args.V, args.D, 80
+    N = 200_000
+    rowptr, gene, label = synthetic_windows(N, V, L)
+    n_tr = int(N * 0.8)
+    W0 = (torch.randn(V, D, device="cuda") / np.sqrt(D)).clamp_(-2 / np.sqrt(D), 2 / np.sqrt(D))
+    Wo0 = torch.randn(D, device="cuda") / np.sqrt(D)
+    tr = torch.randperm(N, device="cuda")[:n_tr].to(torch.int32)
+    alg = n_tr * (L * (8 * D + 4) + 5)
+    os.environ["G2V_CBOW_SLABS"] = "1"
+    for name, env in (("ldg+red (default)", {}), ("tma scatter (UBLKRED)", {"G2V_CBOW_SCATTER": "tma"}),
+                      ("tma gather (UBLKCP)", {"G2V_CBOW_GATHER": "tma"}),
+                      ("tma gather + scatter", {"G2V_CBOW_GATHER": "tma", "G2V_CBOW_SCATTER": "tma"})):
+        for k in ("G2V_CBOW_SCATTER", "G2V_CBOW_GATHER"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        m = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0, lr=0.005)
+        ms, mn = timeit(lambda: m.fwdbwd(tr, n_tr), n=3, warm=2)
+        print(json.dumps({"variant": name, "V": V, "D": D, "fwdbwd_ms": ms, "fwdbwd_ms_min": mn, "alg_GBps": alg / ms / 1e6}), flush=True)
+        del m
+
+
 if __name__ == "__main__":
     p = argparse.ArgumentParser()
-    p.add_argument("what", choices=["slabs", "walk"])
+    p.add_argument("what", choices=["slabs", "walk", "fused"])
     p.add_argument("--reps", type=int, default=2)
     p.add_argument("--V", type=int, default=200_000)
     p.add_argument("--D", type=int, default=512)
@@ -121,4 +146,4 @@ if __name__ == "__main__":
     p.add_argument("--group", type=int, nargs="+", default=[1, 2, 3])
     p.add_argument("--workloads", nargs="+", default=["syn10k", "syn20k", "stress200k"])
     a = p.parse_args()
-    {"slabs": slabs, "walk": walk}[a.what](a)
+    {"slabs": slabs, "walk": walk, "fused": fused}[a.what](a)
