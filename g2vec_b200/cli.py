@@ -217,15 +217,7 @@ def main(argv=None):
             # hence the same --seed split, whatever the number of GPUs)
             r_, l_, k_ = walks.generate_paths(wg, L, args.numRepetition, seed=args.seed, group=i, canonical=True,
                                               walker_begin=rank, walker_stride=world)
-            per = -(-n_total // world)
-            pad_r = torch.full((per, L), paths.PAD, dtype=torch.int32, device=dev); pad_r[:r_.shape[0]] = r_
-            pad_l = torch.zeros(per, dtype=torch.int32, device=dev); pad_l[:l_.shape[0]] = l_
-            pad_k = torch.zeros(per, dtype=torch.int64, device=dev); pad_k[:k_.shape[0]] = k_
-            gr, gl, gk = ([torch.empty_like(t) for _ in range(world)] for t in (pad_r, pad_l, pad_k))
-            dist.all_gather(gr, pad_r); dist.all_gather(gl, pad_l); dist.all_gather(gk, pad_k)
-            for r in range(world):
-                cnt = len(range(r, n_total, world))
-                rows[sl][r::world] = gr[r][:cnt]; lens[sl][r::world] = gl[r][:cnt]; key[sl][r::world] = gk[r][:cnt]
+            rows[sl], lens[sl], key[sl] = paths.gather_walker_shards(dist, world, n_total, r_, l_, k_)
     group = torch.cat([torch.zeros(n_total, dtype=torch.uint8, device=dev), torch.ones(n_total, dtype=torch.uint8, device=dev)])
     w_rowptr, w_gene, w_label, code = paths.build_windows(rows, lens, key, group, n_genes)
     del rows, lens, key, group

@@ -51,6 +51,25 @@ def canonical_rows(nodes, lens=None):
     return rows[perm[first]]
 
 
+def gather_walker_shards(dist, world, n_total, *shards):
+    """Multi-GPU: rank r ran walkers r, r+world, ... (< n_total) and holds ``shards`` (tensors whose first dimension is
+    its walker count).  all_gather them and put every row back at its walker index, so that each rank ends up with
+    the arrays a single GPU would have produced -- same order, hence the same windows order and the same ``--seed``
+    train/validation split whatever the number of GPUs.  Works on any backend (CPU tensors + gloo in the tests)."""
+    per = -(-n_total // world)
+    out = []
+    for t in shards:
+        pad = torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        full = torch.empty((n_total,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        for r in range(world):
+            full[r::world] = parts[r][:len(range(r, n_total, world))]
+        out.append(full)
+    return out
+
+
 def unique_rows(rows, key):
     """The set of G2Vec.py:351 from rows that are ALREADY canonical (sorted, PAD-padded) with their 64-bit keys --
     what ``walks.generate_paths(..., canonical=True)`` returns: first occurrences in ascending key order."""

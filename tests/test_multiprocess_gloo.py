@@ -47,6 +47,14 @@ def _worker(rank, world, port, q):
     assert nodes.shape[0] == n_mine
     gathered = [None] * world
     dist.all_gather_object(gathered, (nodes, wl, sorted(map(int, tr_loc))))
+    # the product's own gather (what the command line does under torchrun): every rank ends up with the 1-GPU arrays
+    from g2vec_b200 import paths
+    full_n, full_l = paths.gather_walker_shards(dist, world, 600, torch.from_numpy(nodes), torch.from_numpy(wl))
+    want_n, want_l = oracle.walks(rp, col, qw, 20, 3, 1, 0, 600)
+    assert (full_n.numpy() == want_n).all() and (full_l.numpy() == want_l).all()
+    # mini-batches: the shuffled list is dealt in order, so batch b is the same set of windows for any world size
+    mb = cbow.shard_by_nnz(tr, lens, world, rank, keep_order=True)
+    assert (mb == tr[rank::world]).all()
     if rank == 0:
         q.put((g.numpy(), go.numpy(), cnt.numpy(), gathered))
     dist.destroy_process_group()
