@@ -13,9 +13,12 @@
 // Graph layouts in HBM (template LAYOUT):
 //   LAY_CSR  rowptr int32 [V+1], col int32 [E], qw uint32 [E]          -- the plain C-ABI arrays (g2v_walk_launch)
 //   LAY_E8   rows int2 {begin,end} [V], edges uint2 {col, qw} [E]      -- one LDG.64 per neighbour
-//   LAY_E4   rows int2 [V], edges uint32 = col | (qw-32768) << 16 [E]  -- V <= 65536 and 32768 <= qw <= 65536
+//   LAY_E4   rows int2 [V], edges uint32 = col | (qw-32768) << 16       -- V <= 65535 and 32768 <= qw <= 65536
 //            (the |PCC| in [0.5, 1] range of the reference's edges, G2Vec.py:389): one LDG.64 brings TWO
-//            neighbours per lane, 64 per warp request
+//            neighbours per lane, 64 per warp request.  Every row starts at an even index and an odd row is
+//            followed by one SENTINEL word (col = V, a node that does not exist): with the bitmap visited set, bit V
+//            is permanently "visited", so the pad word, and the lanes beyond the row (whose register default is the
+//            sentinel word), are masked by the visited test itself -- no validity compares on the hot path
 // g2v_walk_prepare packs the CSR once per graph (the graph is static across all repetitions).
 //
 // Per warp in shared memory: the path (written back once, coalesced) and the visited set -- a V-bit bitmap
@@ -81,19 +84,23 @@ struct WalkGraphPtrs {
 
 // One chunk of a row: lane's neighbours jb + lane*EPL + {0 .. EPL-1}, masked weights (0 = outside [b, e) or
 // already visited) and node ids.  LAY_E4: jb is even (the caller aligns the first chunk down), so the pair
-// is one aligned 8-byte load; the element in front of an odd `b` and the one at `e` are masked out.
+// is one aligned 8-byte load (rows start at even indices; the word after an odd row is a sentinel).
 template <int LAYOUT, bool BITMAP>
 __device__ __forceinline__ void load_chunk(const WalkGraphPtrs &g, int32_t jb, int32_t b, int32_t e, int lane, int hs,
-                                           uint32_t hmask, int hshift, int32_t &c0, int32_t &c1, uint32_t &q0,
-                                           uint32_t &q1) {
+                                           uint32_t hmask, int hshift, uint32_t sent, int32_t &c0, int32_t &c1,
+                                           uint32_t &q0, uint32_t &q1) {
+    (void)b;
     if (LAYOUT == LAY_E4) {
-        const int32_t j = jb + 2 * lane;
-        uint2 w = make_uint2(0u, 0u);
+        const int32_t j = jb + 2 * lane;                                        // even: rows start at even indices
+        uint2 w = make_uint2(sent, sent);                                       // lanes beyond the row: sentinel word
         if (j < e) w = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint32_t *>(g.edges) + j));
         c0 = (int32_t)(w.x & 0xffffu); c1 = (int32_t)(w.y & 0xffffu);
-        const uint32_t a0 = (j >= b && j < e) ? (w.x >> 16) + 32768u : 0u;
-        const uint32_t a1 = (j + 1 < e) ? (w.y >> 16) + 32768u : 0u;           // j + 1 >= b always
-        q0 = unvisited_weight<BITMAP>(hs, hmask, hshift, c0, a0);
+        uint32_t a0 = (w.x >> 16) + 32768u, a1 = (w.y >> 16) + 32768u;
+        if (!BITMAP) {                          // the hash set knows no sentinel: explicit validity
+            a0 = (j < e) ? a0 : 0u;
+            a1 = (j + 1 < e) ? a1 : 0u;
+        }
+        q0 = unvisited_weight<BITMAP>(hs, hmask, hshift, c0, a0);               // bitmap: bit V is always set
         q1 = unvisited_weight<BITMAP>(hs, hmask, hshift, c1, a1);
     } else {
         const int32_t j = jb + lane;
@@ -135,7 +142,11 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
     const int hs = path + Lpad;
     const uint32_t hmask = (uint32_t)H - 1u;
 
-    for (int i = lane; i < H; i += 32) smem[hs + i] = BITMAP ? 0 : -1;
+    constexpr bool SENT = BITMAP && LAYOUT == LAY_E4;   // bit V of the bitmap = a node that is always "visited"
+    const uint32_t sent = (uint32_t)V;                   // sentinel edge word: col = V, weight field 0
+    const int sw = V >> 5;
+    const int32_t sbit = SENT ? (int32_t)(1u << (V & 31)) : 0;
+    for (int i = lane; i < H; i += 32) smem[hs + i] = BITMAP ? ((SENT && i == sw) ? sbit : 0) : -1;
     __syncwarp();
 
     while (true) {
@@ -179,12 +190,12 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
             }
             const uint32_t xlo = __shfl_sync(0xffffffffu, dlo, s & 31), xhi = __shfl_sync(0xffffffffu, dhi, s & 31);
 
-            const int32_t jb0 = EPL == 2 ? (b & ~1) : b;
+            const int32_t jb0 = b;                       // (packed rows start at even indices)
             int32_t nxt;
             if (e - jb0 <= CH) {
                 // ---- short row: one chunk.  One scan gives the total (lane 31) and the prefix sums.
                 int32_t c0, c1; uint32_t q0, q1;
-                load_chunk<LAYOUT, BITMAP>(g, jb0, b, e, lane, hs, hmask, hshift, c0, c1, q0, q1);
+                load_chunk<LAYOUT, BITMAP>(g, jb0, b, e, lane, hs, hmask, hshift, sent, c0, c1, q0, q1);
                 const uint32_t p = q0 + q1;
                 const uint32_t incl = warp_inclusive_scan_u32(p, lane);
                 const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);            // <= 64 * 2^24 < 2^32
@@ -203,7 +214,7 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
                     P[k] = 0; Q0[k] = 0; tot[k] = 0; C0[k] = 0; C1[k] = 0;
                     if (jb0 + k * CH < e) {              // warp-uniform
                         uint32_t q1;
-                        load_chunk<LAYOUT, BITMAP>(g, jb0 + k * CH, b, e, lane, hs, hmask, hshift, C0[k], C1[k], Q0[k], q1);
+                        load_chunk<LAYOUT, BITMAP>(g, jb0 + k * CH, b, e, lane, hs, hmask, hshift, sent, C0[k], C1[k], Q0[k], q1);
                         P[k] = Q0[k] + q1;
                         tot[k] = __reduce_add_sync(0xffffffffu, P[k]);
                         T += tot[k];
@@ -211,7 +222,7 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
                 }
                 for (int32_t jb = jb0 + kKC * CH; jb < e; jb += CH) {
                     int32_t c0, c1; uint32_t q0, q1;
-                    load_chunk<LAYOUT, BITMAP>(g, jb, b, e, lane, hs, hmask, hshift, c0, c1, q0, q1);
+                    load_chunk<LAYOUT, BITMAP>(g, jb, b, e, lane, hs, hmask, hshift, sent, c0, c1, q0, q1);
                     T += __reduce_add_sync(0xffffffffu, q0 + q1);
                 }
                 if (T == 0) break;
@@ -232,7 +243,7 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
                 }
                 for (int32_t jb = jb0 + kKC * CH; !found && jb < e; jb += CH) {
                     int32_t c0, c1; uint32_t q0, q1;
-                    load_chunk<LAYOUT, BITMAP>(g, jb, b, e, lane, hs, hmask, hshift, c0, c1, q0, q1);
+                    load_chunk<LAYOUT, BITMAP>(g, jb, b, e, lane, hs, hmask, hshift, sent, c0, c1, q0, q1);
                     const uint32_t p = q0 + q1;
                     const uint32_t ct = __reduce_add_sync(0xffffffffu, p);
                     if (rem < (unsigned long long)ct) {
@@ -260,12 +271,13 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
             __syncwarp();
             const int B = (H + 31) >> 5, w0 = lane * B, w1 = min(H, w0 + B);
             uint32_t cnt = 0;
-            for (int wi = w0; wi < w1; ++wi) cnt += __popc((uint32_t)smem[hs + wi]);
+            for (int wi = w0; wi < w1; ++wi) cnt += __popc((uint32_t)smem[hs + wi] & ~(uint32_t)((SENT && wi == sw) ? sbit : 0));
             uint32_t pos = warp_inclusive_scan_u32(cnt, lane) - cnt;
             uint64_t h = 0;
             for (int wi = w0; wi < w1; ++wi) {
-                uint32_t bits = (uint32_t)smem[hs + wi];
-                if (bits) smem[hs + wi] = 0;
+                const int32_t keepbit = (SENT && wi == sw) ? sbit : 0;
+                uint32_t bits = (uint32_t)smem[hs + wi] & ~(uint32_t)keepbit;
+                if (bits) smem[hs + wi] = keepbit;
                 while (bits) {
                     const int32_t v = wi * 32 + (__ffs(bits) - 1);
                     bits &= bits - 1;
@@ -310,6 +322,7 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
             if (BITMAP) {
                 __syncwarp();
                 for (int i = lane; i < n; i += 32) smem[hs + (smem[path + i] >> 5)] = 0;   // only the touched words
+                if (SENT) { __syncwarp(); if (lane == 0) smem[hs + sw] = sbit; }
             } else {
                 for (int i = lane; i < H; i += 32) smem[hs + i] = -1;
             }
@@ -329,17 +342,48 @@ __global__ void walk_range_kernel(const uint32_t *__restrict__ qw, int64_t E, in
 }
 
 __global__ void walk_pack_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                                 const uint32_t *__restrict__ qw, int32_t V, int64_t E, int32_t layout,
-                                 int2 *__restrict__ rows, void *__restrict__ edges) {
+                                 const uint32_t *__restrict__ qw, int32_t V, int64_t E, int2 *__restrict__ rows,
+                                 uint2 *__restrict__ e8) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
     for (int64_t v = tid; v < V; v += nth) rows[v] = make_int2(__ldg(rowptr + v), __ldg(rowptr + v + 1));
-    if (layout == LAY_E8) {
-        uint2 *e8 = reinterpret_cast<uint2 *>(edges);
-        for (int64_t j = tid; j < E; j += nth) e8[j] = make_uint2((uint32_t)__ldg(col + j), __ldg(qw + j));
-    } else {
-        uint32_t *e4 = reinterpret_cast<uint32_t *>(edges);
-        for (int64_t j = tid; j < E + 2; j += nth)                       // two pad words: the pair load at E-1
-            e4[j] = j < E ? ((uint32_t)__ldg(col + j) | ((__ldg(qw + j) - 32768u) << 16)) : 0u;
+    for (int64_t j = tid; j < E; j += nth) e8[j] = make_uint2((uint32_t)__ldg(col + j), __ldg(qw + j));
+}
+
+// LAY_E4, step 1 (one block): packed begin of every row = exclusive scan of the degrees rounded up to even.
+__global__ void __launch_bounds__(1024)
+walk_pack4_rows_kernel(const int32_t *__restrict__ rowptr, int32_t V, int2 *__restrict__ rows) {
+    __shared__ int32_t part[1024];
+    const int per = (V + 1023) / 1024, v0 = threadIdx.x * per, v1 = min(V, v0 + per);
+    int32_t sum = 0;
+    for (int v = v0; v < v1; ++v) sum += (rowptr[v + 1] - rowptr[v] + 1) & ~1;
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t acc = 0;
+        for (int t = 0; t < 1024; ++t) { const int32_t x = part[t]; part[t] = acc; acc += x; }
+    }
+    __syncthreads();
+    int32_t pb = part[threadIdx.x];
+    for (int v = v0; v < v1; ++v) {
+        const int32_t deg = rowptr[v + 1] - rowptr[v];
+        rows[v] = make_int2(pb, pb + deg);                            // {even begin, true end}
+        pb += (deg + 1) & ~1;
+    }
+}
+
+// LAY_E4, step 2: one warp per row copies its edges as col | (qw - 32768) << 16; an odd row gets a sentinel word
+__global__ void __launch_bounds__(256)
+walk_pack4_edges_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                        const uint32_t *__restrict__ qw, int32_t V, const int2 *__restrict__ rows,
+                        uint32_t *__restrict__ e4) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t v = warp; v < V; v += nw) {
+        const int32_t b = __ldg(rowptr + v), deg = __ldg(rowptr + v + 1) - b;
+        const int2 r = rows[v];
+        for (int k = lane; k < deg; k += 32)
+            e4[r.x + k] = (uint32_t)__ldg(col + b + k) | ((__ldg(qw + b + k) - 32768u) << 16);
+        if ((deg & 1) && lane == 0) e4[r.y] = (uint32_t)V;
     }
 }
 
@@ -365,7 +409,7 @@ static int launch_walk(const WalkGraphPtrs &g, int layout, int32_t V, int64_t E,
     if (n_walkers == 0) return 0;                                 // empty range: nothing to write
     G2V_REQUIRE(g.rows && out_nodes && out_len && workspace, "%s: null pointer", who);
     G2V_REQUIRE(E == 0 || (g.edges && (layout != LAY_CSR || g.qw)), "%s: null edge arrays with E > 0", who);
-    G2V_REQUIRE(layout == LAY_CSR || layout == LAY_E8 || (layout == LAY_E4 && V <= 65536), "%s: bad layout %d", who, layout);
+    G2V_REQUIRE(layout == LAY_CSR || layout == LAY_E8 || (layout == LAY_E4 && V <= 65535), "%s: bad layout %d", who, layout);
     DeviceProps dp;
     if (device_props(&dp)) return 1;
     G2V_REQUIRE(dp.cc_major == 10, "%s: needs an sm_100 device (found sm_%d%d)", who, dp.cc_major, dp.cc_minor);
@@ -375,7 +419,7 @@ static int launch_walk(const WalkGraphPtrs &g, int layout, int32_t V, int64_t E,
     int Lpad = (L + 31) & ~31;
     if (canon) { Lpad = 32; while (Lpad < L) Lpad <<= 1; }
     // visited set per walker: a V-bit bitmap when a CTA's bitmaps fit 56 KB (>= 4 CTAs per SM), else a hash set
-    const int bm_words = (V + 31) / 32;
+    const int bm_words = (V + 32) / 32;                           // V + 1 bits: bit V is the packed layout's sentinel node
     const char *force = getenv("G2V_WALK_VISITED");               // test hook: "hash" / "bitmap"
     int Hh = 64, hshift = 26;                                     // hash set: >= 3L slots, power of two
     while (Hh < 3 * L) { Hh <<= 1; --hshift; }
@@ -430,10 +474,16 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
                        nullptr, workspace, (cudaStream_t)stream, "g2v_walk_launch");
 }
 
+// 8-byte pairs need 8*E; packed 4-byte words need 4*(E + one sentinel per odd row + the pair load's overhang)
+static size_t packed_edge_bytes(int32_t V, int64_t E) {
+    const size_t a = sizeof(uint2) * (size_t)(E + 2), b = sizeof(uint32_t) * (size_t)(E + V + 4);
+    return a > b ? a : b;
+}
+
 extern "C" int g2v_walk_packed_bytes(int32_t V, int64_t E, size_t *rows_bytes, size_t *edges_bytes) {
     G2V_REQUIRE(V > 0 && E >= 0 && rows_bytes && edges_bytes, "g2v_walk_packed_bytes: bad arguments");
     *rows_bytes = sizeof(int2) * (size_t)V;
-    *edges_bytes = sizeof(uint2) * (size_t)(E + 2);
+    *edges_bytes = packed_edge_bytes(V, E);
     return 0;
 }
 
@@ -446,7 +496,7 @@ extern "C" int g2v_walk_prepare(const int32_t *rowptr, const int32_t *col, const
     cudaStream_t st = (cudaStream_t)stream;
     int layout = LAY_E8;
     const char *force = getenv("G2V_WALK_LAYOUT");                // test hook: "e8" / "e4" (e4 only if eligible)
-    if (V <= 65536 && !(force && force[1] == '8')) {
+    if (V <= 65535 && !(force && force[1] == '8')) {
         int32_t *flag = reinterpret_cast<int32_t *>(workspace) + 8;   // the ticket lives in the first 8 bytes
         int32_t h = 0;
         G2V_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int32_t), st));
@@ -461,12 +511,27 @@ extern "C" int g2v_walk_prepare(const int32_t *rowptr, const int32_t *col, const
         G2V_CUDA_OK(cudaStreamSynchronize(st));                   // setup, once per graph
         if (h == 0) layout = LAY_E4;
     }
-    int64_t work = E + 2 > V ? E + 2 : V;
-    int64_t blocks = (work + 255) / 256;
-    if (blocks > (int64_t)dp.sm_count * 8) blocks = (int64_t)dp.sm_count * 8;
-    walk_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, qw, V, E, layout, reinterpret_cast<int2 *>(rows), edges);
-    G2V_CUDA_OK(cudaGetLastError());
-    count_launch();
+    if (layout == LAY_E4) {
+        // the last pair load of a row may reach one word past its sentinel: zero the buffer's tail words first
+        G2V_CUDA_OK(cudaMemsetAsync(edges, 0, packed_edge_bytes(V, E), st));
+        walk_pack4_rows_kernel<<<1, 1024, 0, st>>>(rowptr, V, reinterpret_cast<int2 *>(rows));
+        G2V_CUDA_OK(cudaGetLastError());
+        int64_t blocks = ((int64_t)V * 32 + 255) / 256;
+        if (blocks > (int64_t)dp.sm_count * 8) blocks = (int64_t)dp.sm_count * 8;
+        walk_pack4_edges_kernel<<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, qw, V, reinterpret_cast<const int2 *>(rows),
+                                                                reinterpret_cast<uint32_t *>(edges));
+        G2V_CUDA_OK(cudaGetLastError());
+        count_launch(2);
+    } else {
+        int64_t work = E > V ? E : V;
+        int64_t blocks = (work + 255) / 256;
+        if (blocks > (int64_t)dp.sm_count * 8) blocks = (int64_t)dp.sm_count * 8;
+        if (blocks < 1) blocks = 1;
+        walk_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, qw, V, E, reinterpret_cast<int2 *>(rows),
+                                                         reinterpret_cast<uint2 *>(edges));
+        G2V_CUDA_OK(cudaGetLastError());
+        count_launch();
+    }
     *layout_out = layout;
     return 0;
 }
@@ -494,7 +559,7 @@ extern "C" int g2v_walk_host(const int32_t *rowptr, const int32_t *col, const ui
     const size_t Ee = (size_t)(E > 0 ? E : 1);
     const size_t o_rp = take(sizeof(int32_t) * (size_t)(V + 1)), o_col = take(sizeof(int32_t) * Ee),
                  o_qw = take(sizeof(uint32_t) * Ee), o_rows = take(sizeof(int2) * (size_t)V),
-                 o_edges = take(sizeof(uint2) * (size_t)(E + 2)), o_nodes = take(sizeof(int32_t) * (size_t)n * (size_t)L),
+                 o_edges = take(packed_edge_bytes(V, E)), o_nodes = take(sizeof(int32_t) * (size_t)n * (size_t)L),
                  o_len = take(sizeof(int32_t) * (size_t)n), o_ws = take(g2v_walk_workspace_bytes());
     char *d = nullptr;
     int rc = 1;

@@ -159,26 +159,32 @@ def test_config1_parity_run_ten_repetitions(g2v):
 
 
 def test_ex_windows_early_stop_run(g2v):
-    """Full reference loop with early stopping; the stop step depends on exact accuracy comparisons
-    (G2Vec.py:276), so it is reported with a tolerance of one step; vectors are compared at the oracle's
-    stop only when both stopped at the same step."""
+    """Full reference loop with early stopping from four different initialisations.  The stop step depends on exact
+    accuracy comparisons (G2Vec.py:276) and the GPU sums in a different float32 order, so a tie may break one step
+    apart; the test records how many of the runs stop on the oracle's step (all of them in every run so far) and
+    compares the vectors of those."""
     (rowptr, gene, label), _ = helpers.ex_windows(reps=2)
     V, D = 7523, 128
     N = len(rowptr) - 1
     tr, va = oracle.split_indices(N, 0)
-    W0, Wo0 = helpers.init_weights(V, D, 0)
-    want, hist, stop, _ = oracle.cbow_train(rowptr, gene, label, tr, va, W0, Wo0, 0.005, max_steps=60)
-    lines = []
-    got, info = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=60, seed=0, W_ih0=W0, W_ho0=Wo0,
-                               log=lines.append, return_info=True)
-    assert lines[0] == "     Start training the modified CBOW with early stopping"
-    assert lines[1].startswith("    - Epoch: 000\tACC[val]=") and lines[-1] == "    Optimization Finish"
-    s_gpu = info["stop_step"]
-    print("stop steps: oracle", stop, "gpu", s_gpu)
-    assert (stop is None) == (s_gpu is None) or abs((stop or 60) - (s_gpu or 60)) <= 1
-    if stop == s_gpu:
-        assert rel_max(got, want) < 5 * RTOL_VEC      # ~40 Adam steps of accumulated reassociation noise
-    assert abs(hist[min(len(hist), len(info["history"])) - 1][1] - info["history"][min(len(hist), len(info["history"])) - 1][1]) < 5e-3
+    same = []
+    for init_seed in range(4):
+        W0, Wo0 = helpers.init_weights(V, D, init_seed)
+        want, hist, stop, _ = oracle.cbow_train(rowptr, gene, label, tr, va, W0, Wo0, 0.005, max_steps=60)
+        lines = []
+        got, info = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=60, seed=0, W_ih0=W0, W_ho0=Wo0,
+                                   log=lines.append, return_info=True)
+        assert lines[0] == "     Start training the modified CBOW with early stopping"
+        assert lines[1].startswith("    - Epoch: 000\tACC[val]=") and lines[-1] == "    Optimization Finish"
+        s_gpu = info["stop_step"]
+        assert (stop is None) == (s_gpu is None) or abs((stop or 60) - (s_gpu or 60)) <= 1, (init_seed, stop, s_gpu)
+        same.append(stop == s_gpu)
+        if stop == s_gpu:
+            assert rel_max(got, want) < 5 * RTOL_VEC      # up to ~40 Adam steps of accumulated reassociation noise
+        k = min(len(hist), len(info["history"])) - 1
+        assert abs(hist[k][1] - info["history"][k][1]) < 5e-3
+    print("early-stop runs on the oracle's step: %d of %d" % (sum(same), len(same)))
+    assert sum(same) >= len(same) - 1
 
 
 @pytest.mark.parametrize("name", ["cbow_small.npz", "cbow_ex.npz"])
