@@ -551,14 +551,17 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic" if args.workload != "ex" else "ex_* graphs (fixture)",
             "config": {"workload": "%s: %s, hidden %d, lenPath %d, numRepetition %d%s" % (
                            args.workload, desc, D, L, reps_total,
-                           " (10 per GPU)" if args.scaling == "weak" and world > 1 else ""),
+                           " (%d per GPU)" % args.reps if args.scaling == "weak" and world > 1 else ""),
                        "windows_train": n_tr_tot, "windows_val": n_va_tot, "mean_window_len": mean_len,
                        "optimizer": args.optimizer, "step": "fwd+bwd+update + val acc + train acc (G2Vec.py:262-267)",
                        "launch": ("one CUDA graph replay per step%s (eager launches: %.3f ms per step)"
                                   % (", NCCL all-reduces inside the graph" if world > 1 else "", main["eager_ms"]))
                                  if main.get("graph") else "eager launches",
                        "parallelism": "dp%d (windows/walkers sharded, W replicated; gradient exchange per step: %s; the 3 "
-                                      "accuracy counters: one 24-byte all_reduce)" % (world, main.get("exchange") or "none"),
+                                      "accuracy counters: %s)" % (
+                                          world, main.get("exchange") or "none",
+                                          "added into every rank's history over NVLS (multimem.red), no NCCL call in the step"
+                                          if (main.get("exchange") or "").startswith("nvl") else "one 24-byte all_reduce"),
                        "l2": "256 MiB flush write before every timed step"},
             "train_only": {"value": n_tr_tot / (upd_ms * 1e-3), "unit": UNIT, "ms_per_step": upd_ms,
                            "note": "fwd+bwd+all-reduce+update, without the two accuracy passes (eager launches)"},

@@ -478,7 +478,21 @@ class DeviceLoop:
         self.n_tr_loc, self.n_va_loc = int(tr_d.shape[0]), int(va_d.shape[0])
         dev = model.device
         self.ctl = torch.zeros(8, dtype=torch.int64, device=dev)
-        self.hist_d = torch.zeros(max(max_epoch, 1) * 4, dtype=torch.int64, device=dev)
+        n_hist = max(max_epoch, 1) * 4
+        # with the NVLink exchange the history lives in symmetric memory and the accuracy counters of all ranks are
+        # added into it by the ranks themselves (g2v_cbow_loop_counters_nvl): no NCCL call is left in the step
+        self.hist_nvl = None
+        if dist and model.nvl:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                h = symm.empty(n_hist, dtype=torch.int64, device=dev)
+                hh = symm.rendezvous(h, dist.group.WORLD)
+                self.hist_nvl = {"h": hh, "mc": int(hh.multicast_ptr or 0) if model.nvl["g_mc"] else 0}
+                self.hist_d = h
+            except Exception:
+                self.hist_nvl = None
+        if self.hist_nvl is None:
+            self.hist_d = torch.zeros(n_hist, dtype=torch.int64, device=dev)
         self.ctl_pin = torch.zeros(8, dtype=torch.int64).pin_memory()
         self.hist_pin = torch.zeros(max(max_epoch, 1) * 4, dtype=torch.int64).pin_memory()
         self.result = model.W_ih.clone()         # snapshot buffer: W_ih before the step being decided
@@ -491,6 +505,10 @@ class DeviceLoop:
     def reset(self):
         _capi.check(self.m.lib.g2v_cbow_loop_init(self.ctl.data_ptr(), self.max_epoch, int(self.early_stop), self._st()),
                     "g2v_cbow_loop_init")
+        if self.hist_nvl:
+            self.hist_nvl["h"].barrier(channel=2)    # no rank is still adding into the history of the previous loop
+            self.hist_d.zero_()
+            self.hist_nvl["h"].barrier(channel=2)    # ... and no rank adds before every history is zero
 
     def attach(self):
         _capi.check(self.m.lib.g2v_cbow_loop_attach(self.ctl.data_ptr()), "g2v_cbow_loop_attach")
@@ -519,9 +537,16 @@ class DeviceLoop:
             m_val.record()
         if show and self.n_tr_loc:
             m.evaluate(self.tr_d, 3)
-        if dist:
+        acc_ptr = m.acc.data_ptr()
+        if self.hist_nvl:
+            hn = self.hist_nvl
+            _capi.check(lib.g2v_cbow_loop_counters_nvl(self.ctl.data_ptr(), acc_ptr, hn["h"].buffer_ptrs_dev, hn["mc"],
+                                                       m.nvl["world"], self._st()), "g2v_cbow_loop_counters_nvl")
+            hn["h"].barrier(channel=3)
+            acc_ptr = None                           # decide on the sums already in hist[step]
+        elif dist:
             dist.all_reduce(m.acc[1:4])
-        _capi.check(lib.g2v_cbow_loop_decide(self.ctl.data_ptr(), m.acc.data_ptr(), self.hist_d.data_ptr(), self._st()),
+        _capi.check(lib.g2v_cbow_loop_decide(self.ctl.data_ptr(), acc_ptr, self.hist_d.data_ptr(), self._st()),
                     "g2v_cbow_loop_decide")
 
     def fetch(self):

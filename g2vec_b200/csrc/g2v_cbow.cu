@@ -521,18 +521,42 @@ loop_begin_kernel(const long long *__restrict__ ctl, long long *__restrict__ acc
     for (int64_t i = (n4 << 2) + tid; i < n; i += nth) S[i] = W[i];
 }
 
+// acc == NULL: the step's counters were already summed over the ranks into hist[step] (loop_counters_nvl_kernel)
 __global__ void loop_decide_kernel(long long *__restrict__ ctl, const long long *__restrict__ acc,
                                    long long *__restrict__ hist) {
     if (ctl[0] != 0) return;
     const long long step = ctl[1];
-    for (int k = 0; k < 4; ++k) hist[step * 4 + k] = acc[k];
-    if (ctl[5] != 0 && acc[2] < ctl[3]) {
+    if (acc)
+        for (int k = 0; k < 4; ++k) hist[step * 4 + k] = acc[k];
+    const long long val = hist[step * 4 + 2];
+    if (ctl[5] != 0 && val < ctl[3]) {
         ctl[0] = 1; ctl[2] = step;                  // dropped: the snapshot taken by loop_begin is the result
     } else {
-        ctl[3] = acc[2];
+        ctl[3] = val;
         if (step + 1 >= ctl[4]) ctl[0] = 1;          // ran --epoch steps without a drop
     }
     ctl[1] = step + 1;
+}
+
+// Multi-GPU: add this rank's three accuracy counters of the current step into hist[step][1..3] of EVERY rank's
+// (symmetric-memory) history -- one multimem.red per counter when the buffer has an NVLS multicast address (the
+// switch applies the add to all replicas), else one system-scope atomic per peer.  Every step has its own slot of
+// the zero-initialised history, so no buffer is ever reset while a peer may still add to or read it.  The caller
+// puts a cross-GPU barrier between this kernel and loop_decide_kernel.
+__global__ void loop_counters_nvl_kernel(const long long *__restrict__ ctl, const long long *__restrict__ acc,
+                                         long long *const *__restrict__ hist_ptrs, long long *__restrict__ hist_mc,
+                                         int32_t world) {
+    if (ctl[0] != 0) return;
+    const int k = 1 + (int)threadIdx.x;              // 3 threads: pre-update train, validation, train counts
+    if (k > 3) return;
+    const long long step = ctl[1], v = acc[k];
+    if (hist_mc) {
+        asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(hist_mc + step * 4 + k), "l"(v) : "memory");
+    } else {
+        for (int p = 0; p < world; ++p)
+            atomicAdd_system(reinterpret_cast<unsigned long long *>(hist_ptrs[p] + step * 4 + k), (unsigned long long)v);
+    }
+    __threadfence_system();
 }
 
 }  // namespace g2v
@@ -569,8 +593,19 @@ extern "C" int g2v_cbow_loop_begin(const int64_t *ctl, int64_t *acc, const float
     return 0;
 }
 
+extern "C" int g2v_cbow_loop_counters_nvl(const int64_t *ctl, const int64_t *acc, int64_t *const *hist_ptrs_dev,
+                                          int64_t *hist_multicast, int32_t world, void *stream) {
+    G2V_REQUIRE(ctl && acc && hist_ptrs_dev && world >= 1, "g2v_cbow_loop_counters_nvl: bad arguments");
+    loop_counters_nvl_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const long long *>(ctl), reinterpret_cast<const long long *>(acc),
+        reinterpret_cast<long long *const *>(hist_ptrs_dev), reinterpret_cast<long long *>(hist_multicast), world);
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
 extern "C" int g2v_cbow_loop_decide(int64_t *ctl, const int64_t *acc, int64_t *hist, void *stream) {
-    G2V_REQUIRE(ctl && acc && hist, "g2v_cbow_loop_decide: null pointer");
+    G2V_REQUIRE(ctl && hist, "g2v_cbow_loop_decide: null pointer");
     loop_decide_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long *>(ctl),
                                                           reinterpret_cast<const long long *>(acc),
                                                           reinterpret_cast<long long *>(hist));

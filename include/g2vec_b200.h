@@ -160,7 +160,7 @@ int g2v_cbow_eval(const int32_t *rowptr, const int32_t *gene, const uint8_t *lab
  *   g2v_cbow_loop_begin: unless stopped, copies W_ih [n floats] into `snapshot` (nullable) -- the weights the
  *        reference would return if this step's validation accuracy drops (:283,:286) -- and zeroes acc[0..3].
  *   g2v_cbow_loop_decide: unless stopped, stores acc[0..3] (loss-sum bits, pre-update train correct, validation
- *        correct, train correct) in hist[step*4 ..], applies `if acc_val < before_acc_val: break` (:276) on the
+ *        correct, train correct) in hist[step*4 ..] (acc == NULL: they are there already, see below), applies `if acc_val < before_acc_val: break` (:276) on the
  *        validation count, else before_val = count (:280); stops after max_steps; step += 1.
  * The host reads ctl / hist whenever it wants to print (every 5th step, :269) instead of after every step.
  * ------------------------------------------------------------------------------------- */
@@ -168,6 +168,12 @@ int g2v_cbow_loop_init(int64_t *ctl, int64_t max_steps, int32_t early_stop, void
 int g2v_cbow_loop_attach(const int64_t *ctl);
 int g2v_cbow_loop_begin(const int64_t *ctl, int64_t *acc, const float *W_ih, float *snapshot, int64_t n, void *stream);
 int g2v_cbow_loop_decide(int64_t *ctl, const int64_t *acc, int64_t *hist, void *stream);
+/* Multi-GPU, hist in symmetric memory (zero-initialised, same size on every rank): add this rank's acc[1..3] into
+ * hist[step][1..3] of every rank (multimem.red through hist_multicast, or system-scope atomics on hist_ptrs_dev);
+ * after a cross-GPU barrier call g2v_cbow_loop_decide with acc == NULL, which then decides on the summed counters
+ * already in hist[step].  Replaces the all_reduce of the counters. */
+int g2v_cbow_loop_counters_nvl(const int64_t *ctl, const int64_t *acc, int64_t *const *hist_ptrs_dev,
+                               int64_t *hist_multicast, int32_t world, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * HOT PATH 2 for tables larger than the L2 (csrc/g2v_cbow_slab.cu): the same step as g2v_cbow_fwdbwd /
