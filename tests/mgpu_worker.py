@@ -37,13 +37,16 @@ def main(out):
             os.environ.pop(k)
         runs[name] = (got, info)
     got, info = runs["nvl"]
+    # the collapsed trainer exchanges c (4*V bytes) with NCCL
+    r1, r1_info = g2v.train_cbow(rowptr, gene, label, 7523, 128, 0.005, max_epoch=11, seed=0, W_ih0=W0, W_ho0=Wo0,
+                                 early_stop=False, log=None, return_info=True, algo="rank1")
     if rank == 0:
         full = np.empty((2 * 7523, 80), np.int32); fl = np.empty(2 * 7523, np.int32)
         for r in range(world):
             full[r::world], fl[r::world] = gathered[r]
         np.savez(out, W=got, hist=np.array(info["history"], dtype=np.float64), nodes=full, lens=fl,
                  graph=np.array(info["graph"]), exchange=np.array([runs[k][1]["exchange"] for k in ("nvl", "nvl_p2p", "nccl")]),
-                 W_p2p=runs["nvl_p2p"][0], W_nccl=runs["nccl"][0],
+                 W_p2p=runs["nvl_p2p"][0], W_nccl=runs["nccl"][0], W_rank1=r1,
                  hist_nccl=np.array(runs["nccl"][1]["history"], dtype=np.float64))
     dist.destroy_process_group()
 

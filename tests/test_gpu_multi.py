@@ -38,7 +38,7 @@ def test_two_gpus_equal_one_gpu(tmp_path):
     assert np.abs(z["W"] - ref).max() < 1e-4 * np.abs(ref).max()
     print("multi-GPU chunks ran as CUDA graphs with the exchange inside:", bool(z["graph"]), "| exchanges:", list(z["exchange"]))
     assert str(z["exchange"][2]).startswith("nccl")
-    for k in ("W_p2p", "W_nccl"):                                  # every gradient-exchange path gives the same vectors
+    for k in ("W_p2p", "W_nccl", "W_rank1"):                       # every exchange path / algorithm gives the same vectors
         assert np.abs(z[k] - ref).max() < 1e-4 * np.abs(ref).max(), k
     assert np.abs(z["W"] - z["W_nccl"]).max() < 2e-5 * np.abs(ref).max()
     assert np.abs(z["hist"] - z["hist_nccl"]).max() <= 2.0 / len(va) + 1e-7
