@@ -93,7 +93,10 @@ __device__ __forceinline__ void load_chunk(const WalkGraphPtrs &g, int32_t jb, i
     if (LAYOUT == LAY_E4) {
         const int32_t j = jb + 2 * lane;                                        // even: rows start at even indices
         uint2 w = make_uint2(sent, sent);                                       // lanes beyond the row: sentinel word
-        if (j < e) w = __ldg(reinterpret_cast<const uint2 *>(reinterpret_cast<const uint32_t *>(g.edges) + j));
+        // predicated load that keeps the register default (a plain `if` makes ptxas branch around the load)
+        asm("{ .reg .pred p; setp.lt.s32 p, %2, %3; @p ld.global.nc.v2.u32 {%0, %1}, [%4]; }"
+                     : "+r"(w.x), "+r"(w.y)
+                     : "r"(j), "r"(e), "l"(reinterpret_cast<const uint32_t *>(g.edges) + j));
         c0 = (int32_t)(w.x & 0xffffu); c1 = (int32_t)(w.y & 0xffffu);
         uint32_t a0 = (w.x >> 16) + 32768u, a1 = (w.y >> 16) + 32768u;
         if (!BITMAP) {                          // the hash set knows no sentinel: explicit validity
