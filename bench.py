@@ -415,7 +415,7 @@ def run_b200(args):
                                   "(%d B) is a separate kernel" % opt_b,
                    "hbm_peak": peak, "frac_of_hbm_peak": gbs / peak, "peak_source": peak_src,
                    "traffic": traffic_lookup("cbow_rows_fwdbwd", args.workload)}
-            if resident and D % 128 == 0 and not r["slabs"]:
+            if resident and D in (128, 256, 512) and not r["slabs"]:
                 pk = l2_rows_peak(r["model"])
                 half = float(ltr.sum()) * D * 4               # bytes gathered = bytes added
                 # the gathers (L2 reads) and the REDs (L2 atomic units) of different warps overlap: the slower of the

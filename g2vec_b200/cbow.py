@@ -420,7 +420,9 @@ def train_cbow(win_rowptr, win_gene, labels, n_genes, hidden, lr, max_epoch=500,
         model.prepare_slabs(va_d)
     if log:
         log("     Start training the modified CBOW with early stopping")
-    if full_batch:
+    if max_epoch <= 0:                           # no optimizer step at all: the initial vectors
+        out, hist, stop = model.W_ih, [], None
+    elif full_batch:
         out, hist, stop = _device_loop(model, dist, tr_d, va_d, n_tr, n_va, len(tr_loc), len(va_loc), max_epoch,
                                        early_stop, log, eval_train, use_graph)
     else:

@@ -66,34 +66,40 @@ __global__ void curand_draws_kernel(uint64_t seed, uint64_t subseq, int32_t n, u
 // float table with one LDG.128 per lane per 512 bytes, or (mode 1) add a constant row into them with
 // red.global.add.v4.f32 -- the two memory operations of the CBOW kernels with the arithmetic removed.  On a table
 // that fits the L2 this is the L2 / L1TEX ceiling the fused kernel is compared with.
-template <int MODE>
+template <int MODE, int VEC>
 __global__ void __launch_bounds__(256)
 l2_rows_kernel(const float *__restrict__ table, float *__restrict__ grad, const int32_t *__restrict__ idx, int64_t n_idx,
-               int32_t VEC, float *__restrict__ sink) {
+               float *__restrict__ sink) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
-    const int D4 = VEC * 32;
+    constexpr int D4 = VEC * 32, UNR = 8 / VEC;          // 8 float4 in flight per lane, as in cbow_rows_kernel
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 one = make_float4(1e-9f, 1e-9f, 1e-9f, 1e-9f);
     for (int64_t base = warp * 32; base < n_idx; base += nwarps * 32) {
         const int cnt = (int)min((int64_t)32, n_idx - base);
         const int32_t g = lane < cnt ? __ldg(idx + base + lane) : 0;
-        for (int k = 0; k < cnt; k += 8) {
-            float4 r[8];
+        for (int k = 0; k < cnt; k += UNR) {
+            float4 r[UNR][VEC];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < UNR; ++u) {
                 const int32_t gk = __shfl_sync(0xffffffffu, g, (k + u) & 31);
+#pragma unroll
                 for (int v = 0; v < VEC; ++v) {
                     if (MODE == 0) {
-                        r[u] = (k + u < cnt) ? __ldg(reinterpret_cast<const float4 *>(table) + (size_t)gk * D4 + v * 32 + lane)
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                        acc.x += r[u].x; acc.y += r[u].y; acc.z += r[u].z; acc.w += r[u].w;
+                        r[u][v] = (k + u < cnt) ? __ldg(reinterpret_cast<const float4 *>(table) + (size_t)gk * D4 + v * 32 + lane)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
                     } else if (k + u < cnt) {
                         float *dst = grad + ((size_t)gk * D4 + v * 32 + lane) * 4;
                         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(one.x), "f"(one.y),
                                      "f"(one.z), "f"(one.w) : "memory");
                     }
                 }
+            }
+            if (MODE == 0) {
+#pragma unroll
+                for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { acc.x += r[u][v].x; acc.y += r[u][v].y; acc.z += r[u][v].z; acc.w += r[u][v].w; }
             }
         }
     }
@@ -111,9 +117,16 @@ extern "C" int g2v_test_l2_rows(const float *table, float *grad, const int32_t *
     if (n_idx == 0) return 0;
     DeviceProps dp;
     if (device_props(&dp)) return 1;
+    G2V_REQUIRE(D == 128 || D == 256 || D == 512, "g2v_test_l2_rows: D must be 128, 256 or 512 (got %d)", D);
     const int grid = dp.sm_count * 8;
-    if (mode == 0) l2_rows_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(table, grad, idx, n_idx, D / 128, sink);
-    else l2_rows_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(table, grad, idx, n_idx, D / 128, sink);
+    cudaStream_t st = (cudaStream_t)stream;
+#define G2V_L2(VEC)                                                                                  \
+    {                                                                                                \
+        if (mode == 0) l2_rows_kernel<0, VEC><<<grid, 256, 0, st>>>(table, grad, idx, n_idx, sink);  \
+        else l2_rows_kernel<1, VEC><<<grid, 256, 0, st>>>(table, grad, idx, n_idx, sink);            \
+    }
+    if (D == 128) G2V_L2(1) else if (D == 256) G2V_L2(2) else G2V_L2(4)
+#undef G2V_L2
     G2V_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

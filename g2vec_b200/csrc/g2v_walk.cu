@@ -54,6 +54,20 @@ constexpr int kKC = 2;          // neighbour chunks kept in registers on the lon
 
 enum { LAY_CSR = 0, LAY_E8 = 1, LAY_E4 = 2 };
 
+// The walker's state is warp-uniform, so inside the step loop every lane stores the SAME value to the SAME shared
+// word (path append, visited insert) and later reads what it stored itself: no divergence and no warp barrier on
+// the instruction-bound path.  compute-sanitizer racecheck reports these same-value stores as warnings (never as
+// errors).  -DG2V_WALK_STRICT_SYNC builds the formally race-free form -- lane 0 stores, __syncwarp() before the
+// warp reads -- which racecheck passes with 0 hazards and which is 15 % more instructions / 20 % slower
+// (profiles/r2/walk_strict_sync_r2x.txt); both forms give bit-identical walks.
+#ifdef G2V_WALK_STRICT_SYNC
+#define G2V_WALK_ONE_WRITER if (lane == 0)
+#define G2V_WALK_STEP_SYNC() __syncwarp()
+#else
+#define G2V_WALK_ONE_WRITER
+#define G2V_WALK_STEP_SYNC()
+#endif
+
 __device__ __forceinline__ uint32_t hash_slot(int32_t c, int shift) {
     return ((uint32_t)c * 2654435761u) >> shift;
 }
@@ -166,8 +180,7 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
         bool dirty = false;
 
         while (true) {
-            // every lane stores the same value: each lane later reads only what it wrote itself
-            smem[path + n] = cur;
+            G2V_WALK_ONE_WRITER smem[path + n] = cur;    // read back only after the walk (epilogue)
             const int32_t s = n++;
             if (s == L - 1) break;                       // the L-th node is appended, never expanded
             int32_t b, e;
@@ -178,14 +191,15 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
                 b = be.x; e = be.y;
             }
             if (b == e) break;                           // no out-edges: dead end
-            if (BITMAP) {                                // visited.insert(cur): same word, same value in every lane
-                smem[hs + (cur >> 5)] |= (1 << (cur & 31));
+            if (BITMAP) {                                // visited.insert(cur)
+                G2V_WALK_ONE_WRITER smem[hs + (cur >> 5)] |= (1 << (cur & 31));
             } else {
                 uint32_t i = hash_slot(cur, hshift);
                 while (smem[hs + i] >= 0) i = (i + 1) & hmask;
-                __syncwarp();                            // every lane has found the free slot before any lane fills it
-                smem[hs + i] = cur;
+                __syncwarp();                            // every lane has found the free slot before it is filled
+                G2V_WALK_ONE_WRITER smem[hs + i] = cur;
             }
+            G2V_WALK_STEP_SYNC();
             dirty = true;
             if ((s & 31) == 0) {                         // 32 steps of 64-bit Philox draws at once, one per lane
                 const uint64_t d = draw64(seed, subseq, (uint32_t)(s + lane));
@@ -262,6 +276,7 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
         }
 
         // ---------------------------------------------------------------- walk finished: n nodes in smem
+        __syncwarp();                                    // lane 0's path stores are visible to the warp
         int32_t *row = out_nodes + (size_t)t * (size_t)L;
         if (!CANON) {
             for (int i = lane; i < L; i += 32) row[i] = (i < n) ? smem[path + i] : -1;     // visit order
@@ -270,7 +285,7 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
             // sorted path.  Lane l owns the words [l*B, (l+1)*B): count, one warp scan for its first output
             // position, then emit its bits in order (and clear the words: the next walker starts from zero).
             const int32_t lastn = smem[path + n - 1];            // the final node is appended but never inserted
-            smem[hs + (lastn >> 5)] |= (1 << (lastn & 31));
+            if (lane == 0) smem[hs + (lastn >> 5)] |= (1 << (lastn & 31));
             __syncwarp();
             const int B = (H + 31) >> 5, w0 = lane * B, w1 = min(H, w0 + B);
             uint32_t cnt = 0;
@@ -322,10 +337,11 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
         }
         if (lane == 0) out_len[t] = n;
         if (dirty) {
-            if (BITMAP) {
+            if (BITMAP) {                                // every lane resets the words it owns (one writer per word)
                 __syncwarp();
-                for (int i = lane; i < n; i += 32) smem[hs + (smem[path + i] >> 5)] = 0;   // only the touched words
-                if (SENT) { __syncwarp(); if (lane == 0) smem[hs + sw] = sbit; }
+                const int B = (H + 31) >> 5, w0 = lane * B, w1 = min(H, w0 + B);
+                for (int wi = w0; wi < w1; ++wi)
+                    if (smem[hs + wi] != 0) smem[hs + wi] = (SENT && wi == sw) ? sbit : 0;
             } else {
                 for (int i = lane; i < H; i += 32) smem[hs + i] = -1;
             }

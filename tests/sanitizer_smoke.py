@@ -41,11 +41,20 @@ def main():
     a, al = g2v.generate_paths_host(rp, col, q, 20, 2, seed=5, group=1)
     assert (a == want).all()
 
-    # glue
+    # glue: exact sort-based path, then the sort-free set pipeline on the sampler's canonical output
     rows = [paths.canonical_rows(*g2v.generate_paths(g2v.WalkGraph(rp, col, qw=q), 20, 2, seed=5, group=grp))
             for grp in (0, 1)]
     prow, plab = paths.integrate(rows[0], rows[1])
     rowptr, gene, label = paths.windows_csr(prow, plab)
+    n = 600
+    r_all = torch.empty((2 * n, 20), dtype=torch.int32, device="cuda")
+    l_all = torch.empty(2 * n, dtype=torch.int32, device="cuda"); k_all = torch.empty(2 * n, dtype=torch.int64, device="cuda")
+    for grp in (0, 1):
+        sl = slice(grp * n, (grp + 1) * n)
+        g2v.generate_paths(g2v.WalkGraph(rp, col, qw=q), 20, 2, seed=5, group=grp, canonical=True, out=(r_all[sl], l_all[sl], k_all[sl]))
+    grp_t = torch.cat([torch.zeros(n, dtype=torch.uint8, device="cuda"), torch.ones(n, dtype=torch.uint8, device="cuda")])
+    rowptr2, gene2, label2, code2 = paths.build_windows(r_all, l_all, k_all, grp_t, 300)
+    assert rowptr2.shape == rowptr.shape and int(rowptr2[-1]) == int(rowptr[-1])
 
     # CBOW: every kernel variant, a few steps
     V = 300
@@ -62,6 +71,15 @@ def main():
                 for k in env:
                     os.environ.pop(k)
                 assert np.isfinite(out).all()
+    # gene-slab passes (forced on the small table), RED and TMA bulk-reduce backward; the device-side loop with early stop
+    for D in (128, 512):
+        W0, Wo0 = helpers.init_weights(V, D, 1)
+        for env in ({"G2V_CBOW_SLABS": "3"}, {"G2V_CBOW_SLABS": "3", "G2V_CBOW_SLAB_SCATTER": "tma", "G2V_CBOW_SLAB_FWD_GROUP": "1"}):
+            os.environ.update(env)
+            out = g2v.train_cbow(rowptr, gene, label, V, D, 0.005, max_epoch=12, seed=0, W_ih0=W0, W_ho0=Wo0, log=None)
+            for k in env:
+                os.environ.pop(k)
+            assert np.isfinite(out).all()
     rp_h, ge_h, la_h = rowptr.cpu().numpy(), gene.cpu().numpy(), label.cpu().numpy()
     W0, Wo0 = helpers.init_weights(V, 128, 1)
     W, Wo = W0.copy(), Wo0.copy()
