@@ -475,7 +475,7 @@ class DeviceLoop:
     reference loop (G2Vec.py:262-267): snapshot + zero counters, fwd+bwd, [all-reduce], optimizer, validation
     accuracy, [training accuracy], [all-reduce of the counters], decide.  Used by train_cbow and by bench.py."""
 
-    def __init__(self, model, dist, tr_d, va_d, n_tr, max_epoch, early_stop):
+    def __init__(self, model, dist, tr_d, va_d, n_tr, max_epoch, early_stop, snapshot=True):
         self.m, self.dist, self.tr_d, self.va_d, self.n_tr = model, dist, tr_d, va_d, n_tr
         self.n_tr_loc, self.n_va_loc = int(tr_d.shape[0]), int(va_d.shape[0])
         dev = model.device
@@ -497,7 +497,8 @@ class DeviceLoop:
             self.hist_d = torch.zeros(n_hist, dtype=torch.int64, device=dev)
         self.ctl_pin = torch.zeros(8, dtype=torch.int64).pin_memory()
         self.hist_pin = torch.zeros(max(max_epoch, 1) * 4, dtype=torch.int64).pin_memory()
-        self.result = model.W_ih.clone()         # snapshot buffer: W_ih before the step being decided
+        # snapshot buffer: W_ih before the step being decided (only an early stop ever returns it)
+        self.result = model.W_ih.clone() if snapshot else None
         self.max_epoch, self.early_stop = int(max_epoch), bool(early_stop)
         self.reset()
 
@@ -522,7 +523,8 @@ class DeviceLoop:
         """Enqueue one iteration (the optional events mark the end of fwd+bwd, of the update, of the validation pass)."""
         m, lib, dist = self.m, self.m.lib, self.dist
         _capi.check(lib.g2v_cbow_loop_begin(self.ctl.data_ptr(), m.acc.data_ptr(), m.W_ih.data_ptr(),
-                                            self.result.data_ptr(), m.V * m.D, self._st()), "g2v_cbow_loop_begin")
+                                            None if self.result is None else self.result.data_ptr(), m.V * m.D,
+                                            self._st()), "g2v_cbow_loop_begin")
         if self.n_tr_loc:
             m.fwdbwd(self.tr_d, self.n_tr)       # acc[1] += correct predictions with the PRE-update weights
         if m_fb is not None:
@@ -576,7 +578,7 @@ def _device_loop(model, dist, tr_d, va_d, n_tr, n_va, n_tr_loc, n_va_loc, max_ep
     Multi-GPU: the all-reduces are part of the captured graph (NCCL is capturable); if capture is refused the
     same launches run eagerly."""
     dev = model.device
-    loop = DeviceLoop(model, dist, tr_d, va_d, n_tr, max_epoch, early_stop)
+    loop = DeviceLoop(model, dist, tr_d, va_d, n_tr, max_epoch, early_stop, snapshot=bool(early_stop))
     shown = lambda s: s % 5 == 0 or eval_train == "always"
     info = _LoopLog(n_tr, n_va, log)
 
