@@ -276,7 +276,7 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
         }
 
         // ---------------------------------------------------------------- walk finished: n nodes in smem
-        __syncwarp();                                    // lane 0's path stores are visible to the warp
+        G2V_WALK_STEP_SYNC();                            // (strict build: lane 0's path stores become visible)
         int32_t *row = out_nodes + (size_t)t * (size_t)L;
         if (!CANON) {
             for (int i = lane; i < L; i += 32) row[i] = (i < n) ? smem[path + i] : -1;     // visit order
@@ -285,7 +285,7 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
             // sorted path.  Lane l owns the words [l*B, (l+1)*B): count, one warp scan for its first output
             // position, then emit its bits in order (and clear the words: the next walker starts from zero).
             const int32_t lastn = smem[path + n - 1];            // the final node is appended but never inserted
-            if (lane == 0) smem[hs + (lastn >> 5)] |= (1 << (lastn & 31));
+            G2V_WALK_ONE_WRITER smem[hs + (lastn >> 5)] |= (1 << (lastn & 31));
             __syncwarp();
             const int B = (H + 31) >> 5, w0 = lane * B, w1 = min(H, w0 + B);
             uint32_t cnt = 0;
