@@ -542,3 +542,43 @@ def test_slab_setup_rejects_unsorted_windows(g2v, monkeypatch):
     m = g2v.CbowModel(rowptr, gene, np.array([0, 1], dtype=np.uint8), 10, 128, W0, Wo0)
     with pytest.raises(RuntimeError, match="not strictly ascending"):
         m.prepare_slabs(None)
+
+
+def test_slab_plan_at_the_stress_table_size_equals_the_single_pass_kernel(g2v, monkeypatch):
+    """BASELINE configs[4]'s table (200k genes x 512 = 410 MB, 3x the L2): g2v_cbow_slab_plan must choose gene slabs on
+    its own, and one step over 40k synthetic windows of 80 distinct genes must give the single-pass kernel's gradient,
+    loss and accuracy counts (same sums, different float32 order), and the same accuracy pass."""
+    import torch
+    V, D, L, N = 200_000, 512, 80, 40_000
+    gen = torch.Generator(device="cuda"); gen.manual_seed(777)
+    x = torch.randint(0, V - L + 1, (N, L), generator=gen, device="cuda", dtype=torch.int32)
+    x, _ = torch.sort(x, dim=1)
+    x += torch.arange(L, device="cuda", dtype=torch.int32)[None, :]
+    label = (torch.rand(N, generator=gen, device="cuda") < 0.5).to(torch.uint8)
+    rowptr = torch.arange(0, (N + 1) * L, L, device="cuda", dtype=torch.int32)
+    gene = x.reshape(-1).contiguous()
+    s = 1.0 / np.sqrt(D)
+    W0 = (torch.randn(V, D, device="cuda", generator=gen) * s).clamp_(-2 * s, 2 * s)
+    Wo0 = (torch.randn(D, device="cuda", generator=gen) * s).clamp_(-2 * s, 2 * s)
+    win = torch.randperm(N, device="cuda", generator=gen)[:32_000].to(torch.int32)
+    m = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0)
+    assert m.prepare_slabs(win) and m._n_slabs >= 4                # the plan decided for slabs by itself
+    m.fwdbwd(win, len(win)); m.evaluate(win, 2)
+    monkeypatch.setenv("G2V_CBOW_SLABS", "1")
+    f = g2v.CbowModel(rowptr, gene, label, V, D, W0, Wo0)
+    assert not f.prepare_slabs(win)
+    f.fwdbwd(win, len(win)); f.evaluate(win, 2)
+    torch.cuda.synchronize()
+    scale = float(f.g_ih.abs().max())
+    assert float((m.g_ih - f.g_ih).abs().max()) < 2e-5 * scale
+    assert float((m.g_ho - f.g_ho).abs().max()) < 2e-5 * float(f.g_ho.abs().max())
+    a, b = m.acc.cpu(), f.acc.cpu()
+    assert abs(int(a[1]) - int(b[1])) <= 2 and abs(int(a[2]) - int(b[2])) <= 2 and int(b[1]) == int(b[2])
+    assert abs(m.loss_sum(a) - f.loss_sum(b)) < 1e-5 * abs(f.loss_sum(b))
+    # size-independent property: rows no window touches have a zero gradient; the touched ones are multiples of W_ho
+    touched = torch.zeros(V, dtype=torch.bool, device="cuda")
+    touched[gene.view(N, L)[win.long()].reshape(-1).long()] = True
+    assert float(m.g_ih[~touched].abs().max()) == 0.0
+    g = m.g_ih[touched][:2000]
+    c = (g @ Wo0) / (Wo0 @ Wo0)                                      # g_ih[row] = c * W_ho  (rank-1 structure, SURVEY 3.2-3)
+    assert float((g - c[:, None] * Wo0[None, :]).abs().max()) < 1e-5 * scale
