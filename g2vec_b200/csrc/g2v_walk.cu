@@ -350,6 +350,204 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
     }
 }
 
+// ---- two walkers per warp (packed edges + bitmap): walk_pair_kernel -----------------------------------------
+// The one-walker kernel is bound by instruction issue, and most of its instructions do the same work whether 32 or
+// 16 lanes take part.  Here each half-warp ("tile") owns a walker and every lane loads FOUR packed neighbours with one
+// LDG.128 (rows are 16-byte aligned and sentinel-padded), so a tile still covers 64 neighbours per request and one
+// instruction stream advances two walkers.  The loop is flat -- one iteration = one step of both tiles, re-converged
+// by __syncwarp() -- and a tile that finishes its walk runs its epilogue / fetches the next ticket while the other
+// waits, so the tiles stay in lock step for the rest of the kernel.  All warp primitives use the tile's lane mask.
+// Same arithmetic as walk_kernel (integer inverse CDF, the walker's own Philox stream): bit-identical output.
+__device__ __forceinline__ uint32_t tile_inclusive_scan_u32(uint32_t v, unsigned tmask) {
+    // 16-lane segments: c = ((32 - 16) << 8): shfl.up clamps at the segment start and p says "source exists"
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1)
+        asm volatile("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0x1000, %2; @p add.u32 %0, %0, t; }"
+                     : "+r"(v) : "r"(o), "r"(tmask));
+    return v;
+}
+
+// full-mask 16-lane-segment scan: both tiles execute it together (converged), each within its own half
+__device__ __forceinline__ uint32_t halfwarp_inclusive_scan_u32(uint32_t v) {
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1)
+        asm volatile("{ .reg .pred p; .reg .u32 t; shfl.sync.up.b32 t|p, %0, %1, 0x1000, 0xffffffff; @p add.u32 %0, %0, t; }"
+                     : "+r"(v) : "r"(o));
+    return v;
+}
+
+// four packed neighbours of one lane: node ids + masked weights (sentinel / visited -> 0)
+struct Quad { uint32_t c0, c1, c2, c3, q0, q1, q2, q3; };
+__device__ __forceinline__ Quad load_quad(const uint4 *__restrict__ e4, int32_t j, int32_t e, bool on, uint32_t sent, int hs) {
+    uint4 w = make_uint4(sent, sent, sent, sent);
+    if (on && j < e) w = __ldg(e4 + (j >> 2));
+    Quad r;
+    r.c0 = w.x & 0xffffu; r.c1 = w.y & 0xffffu; r.c2 = w.z & 0xffffu; r.c3 = w.w & 0xffffu;
+    r.q0 = unvisited_weight<true>(hs, 0u, 0, (int32_t)r.c0, (w.x >> 16) + 32768u);
+    r.q1 = unvisited_weight<true>(hs, 0u, 0, (int32_t)r.c1, (w.y >> 16) + 32768u);
+    r.q2 = unvisited_weight<true>(hs, 0u, 0, (int32_t)r.c2, (w.z >> 16) + 32768u);
+    r.q3 = unvisited_weight<true>(hs, 0u, 0, (int32_t)r.c3, (w.w >> 16) + 32768u);
+    return r;
+}
+
+template <bool CANON>
+__global__ void __launch_bounds__(kWalkWarps * 32, 5)
+walk_pair_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H, uint64_t seed, uint32_t group,
+                 int64_t walker_begin, int64_t n_walkers, int64_t walker_stride, int32_t *__restrict__ out_nodes,
+                 int32_t *__restrict__ out_len, unsigned long long *__restrict__ out_key,
+                 unsigned long long *__restrict__ ticket) {
+    int32_t *const smem = g2v_walk_smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = lane >> 4, tl = lane & 15, tbase = tile << 4;
+    const unsigned tmask = 0xffffu << tbase;
+    const int path = (warp * 2 + tile) * (Lpad + H);
+    const int hs = path + Lpad;
+    const uint32_t sent = (uint32_t)V;
+    const int sw = V >> 5;
+    const int32_t sbit = (int32_t)(1u << (V & 31));
+    const uint4 *__restrict__ e4 = reinterpret_cast<const uint4 *>(g.edges);
+    for (int i = tl; i < H; i += 16) smem[hs + i] = (i == sw) ? sbit : 0;
+    __syncwarp();
+
+    bool have = false, done = false;
+    unsigned long long t = 0;
+    uint64_t subseq = 0;
+    int32_t cur = 0, n = 0;
+    uint32_t dlo = 0, dhi = 0;                           // lane tl holds the draw of step (s & ~15) + tl
+
+    // Everything on the common path is executed by all 32 lanes together with full-mask primitives working inside
+    // 16-lane segments; a tile without work carries sentinel data through it.  Only the per-walk epilogue, the Philox
+    // refill and rows longer than 64 neighbours are tile-divergent sections.
+    while (true) {
+        const bool need = !have && !done;                // take the next walker (rare: once per walk)
+        if (__any_sync(0xffffffffu, need)) {
+            unsigned long long tk = 0;
+            if (need && tl == 0) tk = atomicAdd(ticket, 1ull);
+            tk = __shfl_sync(0xffffffffu, tk, tbase);
+            if (need) {
+                if ((int64_t)tk >= n_walkers) {
+                    done = true;
+                } else {
+                    t = tk;
+                    const int64_t w = walker_begin + (int64_t)tk * walker_stride;
+                    subseq = ((uint64_t)group << 40) + (uint64_t)w;
+                    cur = (int32_t)(w % V);
+                    n = 0; have = true;
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+
+        // ------------------------------------------------------------------ one step of both tiles' walkers
+        const int32_t s = n;
+        if (have) { smem[path + n] = cur; ++n; }         // same value from every lane of the tile
+        bool end = have && (s == L - 1);                 // the L-th node is appended, never expanded
+        bool expand = have && !end;
+        int32_t b = 0, e = 0;
+        if (expand) {
+            const int2 be = __ldg(reinterpret_cast<const int2 *>(g.rows) + cur);
+            b = be.x; e = be.y;
+            if (b == e) { end = true; expand = false; }  // no out-edges: dead end
+        }
+        if (expand) {
+            smem[hs + (cur >> 5)] |= (1 << (cur & 31));  // visited.insert(cur)
+            if ((s & 15) == 0) {                         // 16 steps of 64-bit Philox draws at once, one per lane
+                const uint64_t d = draw64(seed, subseq, (uint32_t)(s + tl));
+                dlo = (uint32_t)d; dhi = (uint32_t)(d >> 32);
+            }
+        }
+        const int src = tbase + (s & 15);
+        const uint32_t xlo = __shfl_sync(0xffffffffu, dlo, src), xhi = __shfl_sync(0xffffffffu, dhi, src);
+        Quad q = load_quad(e4, b + 4 * tl, e, expand, sent, hs);
+        uint32_t p = q.q0 + q.q1 + q.q2 + q.q3;
+        uint32_t incl, r32;
+        bool dead = false;
+        if (__any_sync(0xffffffffu, expand && e - b > 64)) {
+            // ---- a row longer than 64 neighbours in (at least) one tile: tile-divergent two-pass walk over its chunks
+            incl = 0; r32 = 0;
+            if (expand) {
+                unsigned long long T = __reduce_add_sync(tmask, p);
+                for (int32_t jb = b + 64; jb < e; jb += 64) {
+                    const Quad x = load_quad(e4, jb + 4 * tl, e, true, sent, hs);
+                    T += __reduce_add_sync(tmask, x.q0 + x.q1 + x.q2 + x.q3);
+                }
+                if (T == 0) {
+                    dead = true;
+                } else {
+                    unsigned long long rem = __umul64hi(((unsigned long long)xhi << 32) | xlo, T);
+                    int32_t jb = b;
+                    while (true) {
+                        const uint32_t ct = __reduce_add_sync(tmask, p);
+                        if (rem < (unsigned long long)ct) break;
+                        rem -= ct;
+                        jb += 64;
+                        q = load_quad(e4, jb + 4 * tl, e, true, sent, hs);
+                        p = q.q0 + q.q1 + q.q2 + q.q3;
+                    }
+                    r32 = (uint32_t)rem;
+                }
+            }
+            __syncwarp();
+            incl = halfwarp_inclusive_scan_u32(p);
+        } else {
+            incl = halfwarp_inclusive_scan_u32(p);
+            const uint32_t T32 = __shfl_sync(0xffffffffu, incl, tbase + 15);      // <= 64 * 2^16
+            dead = expand && T32 == 0;                   // every neighbour already visited
+            const unsigned long long lo = (unsigned long long)xlo * T32;
+            r32 = (uint32_t)(((unsigned long long)xhi * T32 + (lo >> 32)) >> 32);
+        }
+        const unsigned hit = (__ballot_sync(0xffffffffu, incl > r32) >> tbase) & 0xffffu;
+        const uint32_t before = incl - p;                // weight in front of this lane's four neighbours
+        const uint32_t sel = (before + q.q0 > r32) ? q.c0
+                           : (before + q.q0 + q.q1 > r32) ? q.c1
+                           : (before + q.q0 + q.q1 + q.q2 > r32) ? q.c2 : q.c3;
+        const int32_t nxt = (int32_t)__shfl_sync(0xffffffffu, sel, tbase + (hit ? __ffs(hit) - 1 : 0));
+        if (dead) { end = true; expand = false; }
+        if (expand) cur = nxt;
+
+        if (end) {                                       // ---- walk finished: n nodes in smem (tile-divergent)
+            int32_t *row = out_nodes + (size_t)t * (size_t)L;
+            __syncwarp(tmask);
+            if (!CANON) {
+                for (int i = tl; i < L; i += 16) row[i] = (i < n) ? smem[path + i] : -1;
+                __syncwarp(tmask);
+                const int B = (H + 15) >> 4, w0 = tl * B, w1 = min(H, w0 + B);
+                for (int wi = w0; wi < w1; ++wi)
+                    if (smem[hs + wi] != 0) smem[hs + wi] = (wi == sw) ? sbit : 0;
+            } else {
+                // tuple(sorted(path)) read off the bitmap (see walk_kernel): lane tl owns the words [tl*B, (tl+1)*B)
+                const int32_t lastn = smem[path + n - 1];
+                smem[hs + (lastn >> 5)] |= (1 << (lastn & 31));
+                __syncwarp(tmask);
+                const int B = (H + 15) >> 4, w0 = tl * B, w1 = min(H, w0 + B);
+                uint32_t cnt = 0;
+                for (int wi = w0; wi < w1; ++wi) cnt += __popc((uint32_t)smem[hs + wi] & ~(uint32_t)((wi == sw) ? sbit : 0));
+                uint32_t pos = tile_inclusive_scan_u32(cnt, tmask) - cnt;
+                uint64_t h = 0;
+                for (int wi = w0; wi < w1; ++wi) {
+                    const int32_t keepbit = (wi == sw) ? sbit : 0;
+                    uint32_t bits = (uint32_t)smem[hs + wi] & ~(uint32_t)keepbit;
+                    if (bits) smem[hs + wi] = keepbit;
+                    while (bits) {
+                        const int32_t v = wi * 32 + (__ffs(bits) - 1);
+                        bits &= bits - 1;
+                        row[pos] = v;
+                        h += path_key_term(v, (int)pos);
+                        ++pos;
+                    }
+                }
+                for (int i = n + tl; i < L; i += 16) row[i] = kPathPad;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) h += __shfl_xor_sync(tmask, h, o);
+                if (tl == 0) out_key[t] = path_key_finish(h);
+            }
+            if (tl == 0) out_len[t] = n;
+            have = false;
+        }
+        __syncwarp();                                    // both tiles start the next iteration together
+    }
+}
+
 // ---- graph packing (once per graph) -------------------------------------------------------------
 __global__ void walk_range_kernel(const uint32_t *__restrict__ qw, int64_t E, int32_t *__restrict__ flag) {
     bool bad = false;
@@ -368,13 +566,14 @@ __global__ void walk_pack_kernel(const int32_t *__restrict__ rowptr, const int32
     for (int64_t j = tid; j < E; j += nth) e8[j] = make_uint2((uint32_t)__ldg(col + j), __ldg(qw + j));
 }
 
-// LAY_E4, step 1 (one block): packed begin of every row = exclusive scan of the degrees rounded up to even.
+// LAY_E4, step 1 (one block): packed begin of every row = exclusive scan of the degrees rounded up to 4 entries
+// (16 bytes: walk_pair_kernel loads four neighbours per lane with one LDG.128).
 __global__ void __launch_bounds__(1024)
 walk_pack4_rows_kernel(const int32_t *__restrict__ rowptr, int32_t V, int2 *__restrict__ rows) {
     __shared__ int32_t part[1024];
     const int per = (V + 1023) / 1024, v0 = threadIdx.x * per, v1 = min(V, v0 + per);
     int32_t sum = 0;
-    for (int v = v0; v < v1; ++v) sum += (rowptr[v + 1] - rowptr[v] + 1) & ~1;
+    for (int v = v0; v < v1; ++v) sum += (rowptr[v + 1] - rowptr[v] + 3) & ~3;
     part[threadIdx.x] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -385,12 +584,12 @@ walk_pack4_rows_kernel(const int32_t *__restrict__ rowptr, int32_t V, int2 *__re
     int32_t pb = part[threadIdx.x];
     for (int v = v0; v < v1; ++v) {
         const int32_t deg = rowptr[v + 1] - rowptr[v];
-        rows[v] = make_int2(pb, pb + deg);                            // {even begin, true end}
-        pb += (deg + 1) & ~1;
+        rows[v] = make_int2(pb, pb + deg);                            // {16-byte aligned begin, true end}
+        pb += (deg + 3) & ~3;
     }
 }
 
-// LAY_E4, step 2: one warp per row copies its edges as col | (qw - 32768) << 16; an odd row gets a sentinel word
+// LAY_E4, step 2: one warp per row copies its edges as col | (qw - 32768) << 16; the row is padded with sentinel words
 __global__ void __launch_bounds__(256)
 walk_pack4_edges_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                         const uint32_t *__restrict__ qw, int32_t V, const int2 *__restrict__ rows,
@@ -402,7 +601,7 @@ walk_pack4_edges_kernel(const int32_t *__restrict__ rowptr, const int32_t *__res
         const int2 r = rows[v];
         for (int k = lane; k < deg; k += 32)
             e4[r.x + k] = (uint32_t)__ldg(col + b + k) | ((__ldg(qw + b + k) - 32768u) << 16);
-        if ((deg & 1) && lane == 0) e4[r.y] = (uint32_t)V;
+        if (lane < ((4 - (deg & 3)) & 3)) e4[r.y + lane] = (uint32_t)V;          // sentinel words up to the next multiple of 4
     }
 }
 
@@ -457,6 +656,31 @@ static int launch_walk(const WalkGraphPtrs &g, int layout, int32_t V, int64_t E,
         {{walk_kernel<true, LAY_CSR, false>, walk_kernel<true, LAY_CSR, true>},
          {walk_kernel<true, LAY_E8, false>, walk_kernel<true, LAY_E8, true>},
          {walk_kernel<true, LAY_E4, false>, walk_kernel<true, LAY_E4, true>}}};
+    // two walkers per warp (walk_pair_kernel): packed edges + bitmap, and both tiles' bitmaps within the 56 KB budget
+    const char *ft = getenv("G2V_WALK_TILE");                    // test / A-B hook: "32" / "16" force one / two walkers per warp
+    const size_t pair_smem = 2 * per_warp * (size_t)(Lpad + bm_words);
+    // ... and rows that mostly fit one 64-neighbour request (longer rows take its divergent slow path; measured: syn20k,
+    // mean degree 100, 7.6 ms against 6.4 ms with one walker per warp)
+    const bool short_rows = (double)E <= 56.0 * (double)V;
+    if (layout == LAY_E4 && bitmap && pair_smem <= 56 * 1024 && (ft ? atoi(ft) == 16 : short_rows)) {
+        auto pk = canon ? walk_pair_kernel<true> : walk_pair_kernel<false>;
+        G2V_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
+        G2V_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int per_sm2 = 0;
+        G2V_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, pk, kWalkWarps * 32, pair_smem));
+        G2V_REQUIRE(per_sm2 > 0, "%s: kernel does not fit on an SM", who);
+        int64_t grid2 = (int64_t)dp.sm_count * per_sm2;
+        const int64_t need2 = (n_walkers + 2 * kWalkWarps - 1) / (2 * kWalkWarps);
+        if (grid2 > need2) grid2 = need2;
+        G2V_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(unsigned long long), st));
+        pk<<<(unsigned)grid2, kWalkWarps * 32, pair_smem, st>>>(g, V, L, Lpad, bm_words, seed, group, walker_begin, n_walkers,
+                                                               walker_stride, out_nodes, out_len,
+                                                               reinterpret_cast<unsigned long long *>(out_key),
+                                                               (unsigned long long *)workspace);
+        G2V_CUDA_OK(cudaGetLastError());
+        count_launch();
+        return 0;
+    }
     walk_kern_t kern = table[bitmap][layout][canon];
     // per-device function attributes (set on every call: the process may have switched device)
     G2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
@@ -493,9 +717,9 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
                        nullptr, workspace, (cudaStream_t)stream, "g2v_walk_launch");
 }
 
-// 8-byte pairs need 8*E; packed 4-byte words need 4*(E + one sentinel per odd row + the pair load's overhang)
+// 8-byte pairs need 8*E; packed 4-byte words need 4*(E + up to 3 sentinels per row + the vector load's overhang)
 static size_t packed_edge_bytes(int32_t V, int64_t E) {
-    const size_t a = sizeof(uint2) * (size_t)(E + 2), b = sizeof(uint32_t) * (size_t)(E + V + 4);
+    const size_t a = sizeof(uint2) * (size_t)(E + 2), b = sizeof(uint32_t) * ((size_t)E + 3 * (size_t)V + 8);
     return a > b ? a : b;
 }
 

@@ -160,16 +160,24 @@ def sorted_rows(nodes, lens, pad):
     return out
 
 
-@pytest.mark.parametrize("layout", ["csr", "e8", "e4"])
+@pytest.mark.parametrize("layout", ["csr", "e8", "e4", "e4-one-walker-per-warp"])
 @pytest.mark.parametrize("vis", ["bitmap", "hash"])
 def test_every_layout_and_visited_set_is_bit_exact(g2v, monkeypatch, layout, vis):
-    """Every kernel instantiation: plain CSR arrays (g2v_walk_launch) / {col,qw} pairs / packed 16+16-bit edges
-    (two neighbours per lane) x bitmap / hash visited set x visit order / fused tuple(sorted(path)) epilogue."""
+    """Every kernel instantiation: plain CSR arrays (g2v_walk_launch) / {col,qw} pairs / packed 16+16-bit edges with
+    two walkers per warp (four neighbours per lane) or one (two per lane) x bitmap / hash visited set x visit order /
+    fused tuple(sorted(path)) epilogue."""
     import torch
     from g2vec_b200 import paths
     monkeypatch.setenv("G2V_WALK_VISITED", vis)
     if layout == "e8":
         monkeypatch.setenv("G2V_WALK_LAYOUT", "e8")
+    # packed edges + bitmap: two walkers per warp (walk_pair_kernel, default for rows that mostly fit 64 neighbours)
+    # or one walker per warp; force each so that both run on every graph here, long rows included
+    if layout == "e4-one-walker-per-warp":
+        monkeypatch.setenv("G2V_WALK_TILE", "32")
+        layout = "e4"
+    elif layout == "e4":
+        monkeypatch.setenv("G2V_WALK_TILE", "16")
     cases = [helpers.ex_graph(1) + (80, 2), helpers.random_graph(2000, 40, seed=1, dead_frac=0.2) + (33, 3)]
     V = 300
     A = (0.5 + 0.5 * np.random.RandomState(4).rand(V, V)).astype(np.float32) + np.float32(1e-4)
