@@ -18,7 +18,7 @@ for ln in out.splitlines():
     if m and cur:
         funcs[cur][m.group(1)] += 1
 names = dict(zip(funcs, subprocess.run(["c++filt"] + list(funcs), capture_output=True, text=True).stdout.splitlines()))
-SHIP = ["walk_kernel<true, 2, true>", "walk_kernel<true, 2, false>", "walk_kernel<false, 1, true>", "walk_kernel<true, 0, false>",
+SHIP = ["walk_pair_kernel<true>", "walk_pair_kernel<false>", "walk_kernel<true, 2, true>", "walk_kernel<true, 2, false>", "walk_kernel<false, 1, true>", "walk_kernel<true, 0, false>",
         "cbow_rows_kernel<1, true, false, false>", "cbow_rows_kernel<1, false, false, false>", "cbow_rows_kernel<4, true, false, false>",
         "cbow_rows_kernel<1, true, true, false>", "cbow_rows_kernel<1, true, false, true>",
         "cbow_slab_fwd_kernel<4, 0, false, false>", "cbow_slab_bwd_kernel<4, false>", "cbow_slab_bwd_kernel<4, true>",
