@@ -661,7 +661,11 @@ static int launch_walk(const WalkGraphPtrs &g, int layout, int32_t V, int64_t E,
     const size_t pair_smem = 2 * per_warp * (size_t)(Lpad + bm_words);
     // ... and rows that mostly fit one 64-neighbour request (longer rows take its divergent slow path; measured: syn20k,
     // mean degree 100, 7.6 ms against 6.4 ms with one walker per warp)
+#ifdef G2V_WALK_STRICT_SYNC
+    const bool short_rows = false;                               // the strictly synchronised build keeps one walker per warp
+#else
     const bool short_rows = (double)E <= 56.0 * (double)V;
+#endif
     if (layout == LAY_E4 && bitmap && pair_smem <= 56 * 1024 && (ft ? atoi(ft) == 16 : short_rows)) {
         auto pk = canon ? walk_pair_kernel<true> : walk_pair_kernel<false>;
         G2V_CUDA_OK(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, dp.max_smem_optin));
