@@ -209,7 +209,7 @@ paths_flag_kernel(const int32_t *__restrict__ rows, const unsigned long long *__
     }
 }
 
-constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+constexpr int kScanThreads = 256, kScanItems = 2, kScanTile = kScanThreads * kScanItems;   // small tiles: enough CTAs to fill the chip at 200k rows
 
 // phase A: per-tile totals of (keep, keep*len)
 __global__ void __launch_bounds__(kScanThreads)
