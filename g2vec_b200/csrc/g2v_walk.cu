@@ -660,11 +660,13 @@ static int launch_walk(const WalkGraphPtrs &g, int layout, int32_t V, int64_t E,
     const char *ft = getenv("G2V_WALK_TILE");                    // test / A-B hook: "32" / "16" force one / two walkers per warp
     const size_t pair_smem = 2 * per_warp * (size_t)(Lpad + bm_words);
     // ... and rows that mostly fit one 64-neighbour request (longer rows take its divergent slow path; measured: syn20k,
-    // mean degree 100, 7.6 ms against 6.4 ms with one walker per warp)
+    // mean degree 100, 7.4 ms against 6.4 ms with one walker per warp), on graphs dense enough that walks are long (on
+    // the ex_* graphs, mean degree 3.4 and 62 % of the walks a single node, the per-walk epilogues diverge the tiles:
+    // 0.378 ms against 0.323 ms)
 #ifdef G2V_WALK_STRICT_SYNC
     const bool short_rows = false;                               // the strictly synchronised build keeps one walker per warp
 #else
-    const bool short_rows = (double)E <= 56.0 * (double)V;
+    const bool short_rows = (double)E <= 56.0 * (double)V && (double)E >= 8.0 * (double)V;
 #endif
     if (layout == LAY_E4 && bitmap && pair_smem <= 56 * 1024 && (ft ? atoi(ft) == 16 : short_rows)) {
         auto pk = canon ? walk_pair_kernel<true> : walk_pair_kernel<false>;
