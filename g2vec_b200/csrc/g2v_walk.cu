@@ -12,7 +12,8 @@
 //
 // Graph layouts in HBM (template LAYOUT):
 //   LAY_CSR  rowptr int32 [V+1], col int32 [E], qw uint32 [E]          -- the plain C-ABI arrays (g2v_walk_launch)
-//   LAY_E8   rows int2 {begin,end} [V], edges uint2 {col, qw} [E]      -- one LDG.64 per neighbour
+//   LAY_E8   rows int2 {begin,end} [V], edges uint2 {col, qw}          -- rows start at even indices (an odd row is
+//            followed by one {0, 0} pair: weight 0 masks itself), so one LDG.128 brings TWO neighbours per lane
 //   LAY_E4   rows int2 [V], edges uint32 = col | (qw-32768) << 16       -- V <= 65535 and 32768 <= qw <= 65536
 //            (the |PCC| in [0.5, 1] range of the reference's edges, G2Vec.py:389): one LDG.64 brings TWO
 //            neighbours per lane, 64 per warp request.  Every row starts at an even index and an odd row is
@@ -119,15 +120,18 @@ __device__ __forceinline__ void load_chunk(const WalkGraphPtrs &g, int32_t jb, i
         }
         q0 = unvisited_weight<BITMAP>(hs, hmask, hshift, c0, a0);               // bitmap: bit V is always set
         q1 = unvisited_weight<BITMAP>(hs, hmask, hshift, c1, a1);
+    } else if (LAYOUT == LAY_E8) {
+        const int32_t j = jb + 2 * lane;                                        // even: 16-byte aligned pair of {col, qw}
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);                                   // lanes beyond the row: weight 0
+        if (j < e) w = __ldg(reinterpret_cast<const uint4 *>(g.edges) + (j >> 1));
+        c0 = (int32_t)w.x; c1 = (int32_t)w.z;
+        q0 = unvisited_weight<BITMAP>(hs, hmask, hshift, c0, w.y);
+        q1 = unvisited_weight<BITMAP>(hs, hmask, hshift, c1, (j + 1 < e) ? w.w : 0u);   // (the pad pair has weight 0 too)
     } else {
         const int32_t j = jb + lane;
         uint32_t a0 = 0u;
         c0 = 0;
-        if (LAYOUT == LAY_E8) {
-            uint2 w = make_uint2(0u, 0u);
-            if (j < e) w = __ldg(reinterpret_cast<const uint2 *>(g.edges) + j);
-            c0 = (int32_t)w.x; a0 = w.y;
-        } else if (j < e) {
+        if (j < e) {
             c0 = __ldg(reinterpret_cast<const int32_t *>(g.edges) + j);
             a0 = __ldg(g.qw + j);
         }
@@ -152,7 +156,7 @@ walk_kernel(const WalkGraphPtrs g, int32_t V, int32_t L, int32_t Lpad, int32_t H
             int32_t *__restrict__ out_nodes, int32_t *__restrict__ out_len, unsigned long long *__restrict__ out_key,
             unsigned long long *__restrict__ ticket) {
     int32_t *const smem = g2v_walk_smem;
-    constexpr int EPL = LAYOUT == LAY_E4 ? 2 : 1;       // neighbours per lane per chunk
+    constexpr int EPL = LAYOUT == LAY_CSR ? 1 : 2;      // neighbours per lane per chunk
     constexpr int CH = 32 * EPL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int path = warp * (Lpad + H);                  // offsets into smem (ints), not pointers
@@ -558,22 +562,30 @@ __global__ void walk_range_kernel(const uint32_t *__restrict__ qw, int64_t E, in
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
 
-__global__ void walk_pack_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                                 const uint32_t *__restrict__ qw, int32_t V, int64_t E, int2 *__restrict__ rows,
-                                 uint2 *__restrict__ e8) {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t v = tid; v < V; v += nth) rows[v] = make_int2(__ldg(rowptr + v), __ldg(rowptr + v + 1));
-    for (int64_t j = tid; j < E; j += nth) e8[j] = make_uint2((uint32_t)__ldg(col + j), __ldg(qw + j));
+// LAY_E8, step 2: one warp per row copies its edges as {col, qw} pairs; an odd row is followed by a {0, 0} pair
+// (the buffer is zeroed first).
+__global__ void __launch_bounds__(256)
+walk_pack8_edges_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                        const uint32_t *__restrict__ qw, int32_t V, const int2 *__restrict__ rows,
+                        uint2 *__restrict__ e8) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t v = warp; v < V; v += nw) {
+        const int32_t b = __ldg(rowptr + v), deg = __ldg(rowptr + v + 1) - b;
+        const int2 r = rows[v];
+        for (int k = lane; k < deg; k += 32) e8[r.x + k] = make_uint2((uint32_t)__ldg(col + b + k), __ldg(qw + b + k));
+    }
 }
 
-// LAY_E4, step 1 (one block): packed begin of every row = exclusive scan of the degrees rounded up to 4 entries
-// (16 bytes: walk_pair_kernel loads four neighbours per lane with one LDG.128).
+// Packed layouts, step 1 (one block): packed begin of every row = exclusive scan of the degrees rounded up to `align`
+// entries = 16 bytes (E4: four 4-byte words, E8: two 8-byte pairs), so that rows can be read with LDG.128.
 __global__ void __launch_bounds__(1024)
-walk_pack4_rows_kernel(const int32_t *__restrict__ rowptr, int32_t V, int2 *__restrict__ rows) {
+walk_pack_rows_kernel(const int32_t *__restrict__ rowptr, int32_t V, int32_t align, int2 *__restrict__ rows) {
+    const int32_t am = align - 1;                        // rows start at multiples of `align` entries (2: E8, 4: E4)
     __shared__ int32_t part[1024];
     const int per = (V + 1023) / 1024, v0 = threadIdx.x * per, v1 = min(V, v0 + per);
     int32_t sum = 0;
-    for (int v = v0; v < v1; ++v) sum += (rowptr[v + 1] - rowptr[v] + 3) & ~3;
+    for (int v = v0; v < v1; ++v) sum += (rowptr[v + 1] - rowptr[v] + am) & ~am;
     part[threadIdx.x] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -585,7 +597,7 @@ walk_pack4_rows_kernel(const int32_t *__restrict__ rowptr, int32_t V, int2 *__re
     for (int v = v0; v < v1; ++v) {
         const int32_t deg = rowptr[v + 1] - rowptr[v];
         rows[v] = make_int2(pb, pb + deg);                            // {16-byte aligned begin, true end}
-        pb += (deg + 3) & ~3;
+        pb += (deg + am) & ~am;
     }
 }
 
@@ -723,9 +735,9 @@ extern "C" int g2v_walk_launch(const int32_t *rowptr, const int32_t *col, const 
                        nullptr, workspace, (cudaStream_t)stream, "g2v_walk_launch");
 }
 
-// 8-byte pairs need 8*E; packed 4-byte words need 4*(E + up to 3 sentinels per row + the vector load's overhang)
+// 8-byte pairs need 8*(E + one pad pair per odd row); packed 4-byte words 4*(E + up to 3 sentinels per row + overhang)
 static size_t packed_edge_bytes(int32_t V, int64_t E) {
-    const size_t a = sizeof(uint2) * (size_t)(E + 2), b = sizeof(uint32_t) * ((size_t)E + 3 * (size_t)V + 8);
+    const size_t a = sizeof(uint2) * ((size_t)E + (size_t)V + 4), b = sizeof(uint32_t) * ((size_t)E + 3 * (size_t)V + 8);
     return a > b ? a : b;
 }
 
@@ -738,7 +750,7 @@ extern "C" int g2v_walk_packed_bytes(int32_t V, int64_t E, size_t *rows_bytes, s
 
 extern "C" int g2v_walk_prepare(const int32_t *rowptr, const int32_t *col, const uint32_t *qw, int32_t V, int64_t E,
                                 void *rows, void *edges, int32_t *layout_out, void *workspace, void *stream) {
-    G2V_REQUIRE(V > 0 && E >= 0 && E < (1ll << 31), "g2v_walk_prepare: bad sizes (V=%d E=%lld)", V, (long long)E);
+    G2V_REQUIRE(V > 0 && E >= 0 && E + 3ll * V + 8 < (1ll << 31), "g2v_walk_prepare: bad sizes (V=%d E=%lld)", V, (long long)E);
     G2V_REQUIRE(rowptr && rows && edges && layout_out && workspace && (E == 0 || (col && qw)), "g2v_walk_prepare: null pointer");
     DeviceProps dp;
     if (device_props(&dp)) return 1;
@@ -760,27 +772,20 @@ extern "C" int g2v_walk_prepare(const int32_t *rowptr, const int32_t *col, const
         G2V_CUDA_OK(cudaStreamSynchronize(st));                   // setup, once per graph
         if (h == 0) layout = LAY_E4;
     }
-    if (layout == LAY_E4) {
-        // the last pair load of a row may reach one word past its sentinel: zero the buffer's tail words first
-        G2V_CUDA_OK(cudaMemsetAsync(edges, 0, packed_edge_bytes(V, E), st));
-        walk_pack4_rows_kernel<<<1, 1024, 0, st>>>(rowptr, V, reinterpret_cast<int2 *>(rows));
-        G2V_CUDA_OK(cudaGetLastError());
-        int64_t blocks = ((int64_t)V * 32 + 255) / 256;
-        if (blocks > (int64_t)dp.sm_count * 8) blocks = (int64_t)dp.sm_count * 8;
+    // pads / overhang read as weight-0 (E8) or are overwritten with sentinels (E4): zero the whole buffer first
+    G2V_CUDA_OK(cudaMemsetAsync(edges, 0, packed_edge_bytes(V, E), st));
+    walk_pack_rows_kernel<<<1, 1024, 0, st>>>(rowptr, V, layout == LAY_E4 ? 4 : 2, reinterpret_cast<int2 *>(rows));
+    G2V_CUDA_OK(cudaGetLastError());
+    int64_t blocks = ((int64_t)V * 32 + 255) / 256;
+    if (blocks > (int64_t)dp.sm_count * 8) blocks = (int64_t)dp.sm_count * 8;
+    if (layout == LAY_E4)
         walk_pack4_edges_kernel<<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, qw, V, reinterpret_cast<const int2 *>(rows),
                                                                 reinterpret_cast<uint32_t *>(edges));
-        G2V_CUDA_OK(cudaGetLastError());
-        count_launch(2);
-    } else {
-        int64_t work = E > V ? E : V;
-        int64_t blocks = (work + 255) / 256;
-        if (blocks > (int64_t)dp.sm_count * 8) blocks = (int64_t)dp.sm_count * 8;
-        if (blocks < 1) blocks = 1;
-        walk_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, qw, V, E, reinterpret_cast<int2 *>(rows),
-                                                         reinterpret_cast<uint2 *>(edges));
-        G2V_CUDA_OK(cudaGetLastError());
-        count_launch();
-    }
+    else
+        walk_pack8_edges_kernel<<<(unsigned)blocks, 256, 0, st>>>(rowptr, col, qw, V, reinterpret_cast<const int2 *>(rows),
+                                                                reinterpret_cast<uint2 *>(edges));
+    G2V_CUDA_OK(cudaGetLastError());
+    count_launch(2);
     *layout_out = layout;
     return 0;
 }
